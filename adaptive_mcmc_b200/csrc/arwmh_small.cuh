@@ -1,0 +1,320 @@
+// arwmh_small.cuh -- thread-per-chain fused ARWMH kernel for small dimensions (d <= ~12).
+//
+// One thread owns one chain for the whole launch: position, energy, running mean, the proposal
+// factor and the step size live in REGISTERS across all K fused steps; HBM is touched once at
+// launch start / end (struct-of-arrays, chain index fastest => every access is coalesced) plus
+// the thinned sample stream.  This is what moves eight_schools off the 624 B/step HBM roofline
+//  onto the FP32/SFU issue rate.
+//
+// The proposal factor is carried as LDL^T:  L = Lt * diag(sqrt(Dg)),  Lt unit lower triangular.
+// The reference (python/kernels/arwmh.py:190 -> NumPyro cholesky_update) converts L -> (L/diag, diag^2),
+// runs the rank-one recurrence and converts back on EVERY step; carrying (Lt, Dg) across the
+// fused steps removes both conversions and all but one reciprocal per column.  For K = 1 the
+// arithmetic is the reference's sequence exactly.
+#pragma once
+#include "common.cuh"
+#include "models.cuh"
+
+namespace amcmc {
+
+template <typename R, int D> struct ChainRegs {
+  static constexpr int NL = D * (D - 1) / 2;
+  R x[D];
+  R mu[D];
+  R Lt[NL > 0 ? NL : 1];  // strictly-lower part of the unit-diagonal factor, row-major packed
+  R Dg[D];                // squared diagonal
+  R U, lam, macc, asc;
+};
+
+AMCMC_HD constexpr int tri_strict(int i, int j) { return i * (i - 1) / 2 + j; }  // i > j
+AMCMC_HD constexpr int tri_full(int i, int j) { return i * (i + 1) / 2 + j; }    // i >= j
+
+// Rank-one update  Lt Dg Lt^T <- (1-gamma) Lt Dg Lt^T + gamma w w^T   (Gill-Golub-Murray-Saunders
+// C1 recurrence, algebraically NumPyro's cholesky_update(sqrt(1-gamma) L, w, gamma) with t = 1/b):
+//   g = D_j + c w_j^2 t;  D_j' = g;  coef = c w_j t / g;  t <- D_j t / g;
+//   w_i -= w_j Lt_ij;  Lt_ij += coef w_i   (i > j)
+// WANT additionally accumulates |L' e^lam' - L e^lam|_F^2 (arwmh.py:197) on the fly.
+template <typename R, int D, bool WANT>
+AMCMC_HD R rank1_sweep(ChainRegs<R, D>& s, R (&w)[D], R gamma, R el_old, R el_new) {
+  R t = (R)1;
+  const R omg = (R)1 - gamma;
+  R ss = (R)0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const R Dold = s.Dg[j];
+    const R Dj = omg * Dold;
+    const R wj = w[j];
+    const R cw = gamma * wj;
+    const R g = fma(cw * wj, t, Dj);
+    const R tr = t * Num<R>::rcp(g);
+    const R coef = cw * tr;
+    t = Dj * tr;
+    s.Dg[j] = g;
+    R so = 0, sn = 0;
+    if (WANT) {
+      so = Num<R>::sqrt(Dold) * el_old;
+      sn = Num<R>::sqrt(g) * el_new;
+      const R dd = sn - so;
+      ss = fma(dd, dd, ss);
+    }
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) {
+      const R Lo = s.Lt[tri_strict(i, j)];
+      w[i] = fma(-wj, Lo, w[i]);
+      const R Ln = fma(coef, w[i], Lo);
+      s.Lt[tri_strict(i, j)] = Ln;
+      if (WANT) {
+        const R df = fma(Ln, sn, -(Lo * so));
+        ss = fma(df, df, ss);
+      }
+    }
+  }
+  return ss;
+}
+
+// |L|_F^2 of the current factor (used when the factor is kept: as_change = |e^lam' - e^lam| |L|_F)
+template <typename R, int D> AMCMC_HD R factor_frob2(const ChainRegs<R, D>& s) {
+  R ss = 0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    R col = (R)1;
+#pragma unroll
+    for (int i = j + 1; i < D; ++i) col = fma(s.Lt[tri_strict(i, j)], s.Lt[tri_strict(i, j)], col);
+    ss = fma(s.Dg[j], col, ss);
+  }
+  return ss;
+}
+
+struct StepConsts {
+  // filled per step (chain-independent)
+  bool n_is_one;
+};
+
+// One ARWMH.sample (python/kernels/arwmh.py:140-207) for the chain held in `s`.
+template <class Model, typename R, bool ADAPT>
+AMCMC_HD bool arwmh_step(ChainRegs<R, Model::D>& s, const Model& m, const R (&z)[Model::D], R u, R nf,
+                         bool n_is_one, R lr_decay, R target, R eps, bool want_asc) {
+  constexpr int D = Model::D;
+  const R el = Num<R>::exp(s.lam);
+  // :166-167  x' = x + (L e^lam + eps I) z,  L z = Lt (sqrt(Dg) .* z)
+  R y[D], xp[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) y[j] = z[j] * Num<R>::sqrt(s.Dg[j]);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    R acc = y[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) acc = fma(s.Lt[tri_strict(i, j)], y[j], acc);
+    xp[i] = s.x[i] + fma(el, acc, eps * z[i]);
+  }
+  // :170-171
+  R Up = m.potential(xp);
+  if (Num<R>::isnan(Up)) Up = Num<R>::inf();
+  // :173-178   clip(exp(.), max=1) keeps NaN
+  const R e = Num<R>::exp(s.U - Up);
+  const R alpha = (e > (R)1) ? (R)1 : e;
+  const bool acc = u < alpha;
+#pragma unroll
+  for (int k = 0; k < D; ++k) s.x[k] = acc ? xp[k] : s.x[k];
+  s.U = acc ? Up : s.U;
+  // :185
+  s.macc = fma(alpha - s.macc, Num<R>::rcp(nf), s.macc);
+  if (!ADAPT) return acc;
+  // :183, :188-193
+  const R gamma = n_is_one ? (R)1 : Num<R>::pow_neg(nf, lr_decay);
+  R w[D];
+  bool ok = !n_is_one;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const R dl = s.x[k] - s.mu[k];
+    s.mu[k] = fma(gamma, dl, s.mu[k]);
+    w[k] = dl;
+    ok = ok && (Num<R>::abs(dl) < Num<R>::kBig) && (s.Dg[k] > (R)0);
+  }
+  const R lam_new = fma(gamma, alpha - target, s.lam);
+  // :190-191 rank-one update; "NaN => keep the old factor" is applied as a pre-condition
+  // (gamma == 1 <=> zero scaled diagonal, non-positive pivot, non-finite delta), see DESIGN.md.
+  if (want_asc) {
+    const R el_new = Num<R>::exp(lam_new);
+    R ss;
+    if (ok) {
+      ss = rank1_sweep<R, D, true>(s, w, gamma, el, el_new);
+    } else {
+      const R de = el_new - el;
+      ss = de * de * factor_frob2(s);
+    }
+    s.asc = Num<R>::sqrt(ss);  // :197
+  } else if (ok) {
+    rank1_sweep<R, D, false>(s, w, gamma, el, el);
+  }
+  s.lam = lam_new;
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-side views of amcmc_state / amcmc_run_args
+// ---------------------------------------------------------------------------------------------
+template <typename R> struct StateView {
+  int64_t C;
+  R *z, *pe, *macc, *loc, *scale, *lam, *asc;
+};
+
+template <typename R> struct RunView {
+  int64_t i0, n_steps, thinning, collect_start, num_warmup;
+  R lr_decay, target, eps;
+  uint64_t seed;
+  int64_t chain_offset;
+  const R* normals;
+  const R* uniforms;
+  R* out_z;
+  R* out_pe;
+  uint8_t* out_acc;
+};
+
+template <typename R, int D>
+AMCMC_HD void load_chain(ChainRegs<R, D>& s, const StateView<R>& st, int64_t c) {
+  const int64_t C = st.C;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    s.x[k] = st.z[k * C + c];
+    s.mu[k] = st.loc[k * C + c];
+  }
+  R inv_diag[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const R dg = st.scale[tri_full(j, j) * C + c];
+    s.Dg[j] = dg * dg;
+    inv_diag[j] = (R)1 / dg;
+  }
+#pragma unroll
+  for (int i = 1; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) s.Lt[tri_strict(i, j)] = st.scale[tri_full(i, j) * C + c] * inv_diag[j];
+  s.U = st.pe[c];
+  s.lam = st.lam[c];
+  s.macc = st.macc[c];
+  s.asc = st.asc[c];
+}
+
+template <typename R, int D, bool ADAPT>
+AMCMC_HD void store_chain(const ChainRegs<R, D>& s, const StateView<R>& st, int64_t c) {
+  const int64_t C = st.C;
+#pragma unroll
+  for (int k = 0; k < D; ++k) st.z[k * C + c] = s.x[k];
+  st.pe[c] = s.U;
+  if (!ADAPT) return;
+#pragma unroll
+  for (int k = 0; k < D; ++k) st.loc[k * C + c] = s.mu[k];
+  R sd[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    sd[j] = ::sqrt(s.Dg[j]);
+    st.scale[tri_full(j, j) * C + c] = sd[j];
+  }
+#pragma unroll
+  for (int i = 1; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) st.scale[tri_full(i, j) * C + c] = s.Lt[tri_strict(i, j)] * sd[j];
+  st.lam[c] = s.lam;
+  st.macc[c] = s.macc;
+  st.asc[c] = s.asc;
+}
+
+// The whole per-chain launch body (host-compilable for tests/hostsim).
+template <class Model, typename R, bool ADAPT, bool EXTERNAL>
+AMCMC_HD void arwmh_chain_run(const Model& m, const StateView<R>& st, const RunView<R>& a, int64_t c) {
+  constexpr int D = Model::D;
+  const int64_t C = st.C;
+  ChainRegs<R, D> s;
+  load_chain(s, st, c);
+  const Philox rng(a.seed, (uint64_t)(c + a.chain_offset));
+  int64_t until_collect = a.collect_start + a.thinning;
+  int64_t sidx = 0;
+  for (int64_t t = 0; t < a.n_steps; ++t) {
+    const int64_t i = a.i0 + t;
+    R z[D], u;
+    if (EXTERNAL) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) z[k] = a.normals[(t * D + k) * C + c];
+      u = a.uniforms[t * C + c];
+    } else {
+      philox_draws<R, D>(rng, (uint64_t)i, z, u);
+    }
+    // :180-181  n restarts at 1 after warmup
+    const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
+    const bool last = (t == a.n_steps - 1);
+    const bool acc = arwmh_step<Model, R, ADAPT>(s, m, z, u, (R)n, n == 1, a.lr_decay, a.target, a.eps, last);
+    if (a.out_acc) a.out_acc[t * C + c] = (uint8_t)acc;
+    if (--until_collect == 0) {
+      until_collect = a.thinning;
+      if (a.out_z) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) a.out_z[(sidx * D + k) * C + c] = s.x[k];
+      }
+      if (a.out_pe) a.out_pe[sidx * C + c] = s.U;
+      ++sidx;
+    }
+  }
+  store_chain<R, D, ADAPT>(s, st, c);
+}
+
+#ifdef __CUDACC__
+template <class Model, typename R, bool ADAPT, bool EXTERNAL>
+__global__ void __launch_bounds__(64, (sizeof(R) == 4 ? 7 : 1))
+arwmh_small_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= st.C) return;
+  arwmh_chain_run<Model, R, ADAPT, EXTERNAL>(m, st, a, c);
+}
+
+// ARWMH.init (python/kernels/arwmh.py:111-136): q0 ~ U(-r, r)^d (unless given), U0, loc = q0, scale = I, ...
+template <class Model, typename R>
+__global__ void arwmh_small_init_kernel(const Model m, const StateView<R> st, uint64_t seed, int64_t chain_offset,
+                                        R radius, int use_given_z) {
+  constexpr int D = Model::D;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t C = st.C;
+  if (c >= C) return;
+  R q[D];
+  if (use_given_z) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) q[k] = st.z[k * C + c];
+  } else {
+    const Philox rng(seed, (uint64_t)(c + chain_offset));
+    constexpr int NBLK = (D + 3) / 4;
+#pragma unroll
+    for (int b = 0; b < NBLK; ++b) {
+      uint32_t o[4];
+      rng.block(kInitStep, (uint32_t)b, o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (4 * b + k < D) q[4 * b + k] = (R)((word_to_uniform(o[k]) * 2.0f - 1.0f) * (float)radius);
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) st.z[k * C + c] = q[k];
+  }
+  st.pe[c] = m.potential(q);
+#pragma unroll
+  for (int k = 0; k < D; ++k) st.loc[k * C + c] = q[k];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) st.scale[tri_full(i, j) * C + c] = (i == j) ? (R)1 : (R)0;
+  st.lam[c] = 0;
+  st.macc[c] = 0;
+  st.asc[c] = 0;
+}
+
+template <class Model, typename R>
+__global__ void potential_small_kernel(const Model m, int64_t n, const R* __restrict__ q, R* __restrict__ out) {
+  constexpr int D = Model::D;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  R x[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) x[k] = q[k * n + c];
+  out[c] = m.potential(x);
+}
+#endif  // __CUDACC__
+
+}  // namespace amcmc

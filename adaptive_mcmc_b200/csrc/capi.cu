@@ -1,0 +1,289 @@
+// capi.cu -- the C ABI declared in include/amcmc.h: handle management, argument validation,
+// family dispatch and the host-buffer entry point.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include "internal.h"
+
+namespace amcmc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return AMCMC_OK;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return AMCMC_ERR_CUDA;
+}
+
+static size_t elt(int dtype) { return dtype == AMCMC_F64 ? 8 : 4; }
+
+// host float64 -> device array of `dtype`
+static int upload(const double* src, int64_t n, int dtype, void** out) {
+  *out = nullptr;
+  if (n <= 0) return AMCMC_OK;
+  int rc = check_cuda(cudaMalloc(out, (size_t)n * elt(dtype)), "cudaMalloc(model array)");
+  if (rc) return rc;
+  if (dtype == AMCMC_F64) return check_cuda(cudaMemcpy(*out, src, (size_t)n * 8, cudaMemcpyHostToDevice), "cudaMemcpy");
+  std::vector<float> tmp((size_t)n);
+  for (int64_t i = 0; i < n; ++i) tmp[(size_t)i] = (float)src[i];
+  return check_cuda(cudaMemcpy(*out, tmp.data(), (size_t)n * 4, cudaMemcpyHostToDevice), "cudaMemcpy");
+}
+
+static const double kLog2PiHalfH = 0.91893853320467274178;
+
+}  // namespace amcmc
+
+using namespace amcmc;
+
+extern "C" {
+
+const char* amcmc_last_error(void) { return g_err; }
+int amcmc_version(void) { return AMCMC_VERSION; }
+
+int amcmc_model_create(amcmc_model** out, int model_id, int dtype, int dim, int n_arrays,
+                       const double* const* arrays, const int64_t* lens) {
+  if (!out) { set_error("amcmc_model_create: out is NULL"); return AMCMC_ERR_ARG; }
+  *out = nullptr;
+  if (dtype != AMCMC_F32 && dtype != AMCMC_F64) { set_error("bad dtype %d", dtype); return AMCMC_ERR_ARG; }
+  if (n_arrays < 0 || n_arrays > 4 || (n_arrays > 0 && (!arrays || !lens))) {
+    set_error("bad n_arrays %d / NULL arrays", n_arrays);
+    return AMCMC_ERR_ARG;
+  }
+  amcmc_model* m = (amcmc_model*)calloc(1, sizeof(amcmc_model));
+  m->model_id = model_id;
+  m->dtype = dtype;
+  m->dim = dim;
+  m->n_arrays = n_arrays;
+  int rc = check_cuda(cudaGetDevice(&m->device), "cudaGetDevice");
+  if (rc) { free(m); return rc; }
+  switch (model_id) {
+    case AMCMC_MODEL_STD_NORMAL:
+      if (dim < 1) { set_error("std_normal: dim must be >= 1"); rc = AMCMC_ERR_ARG; }
+      break;
+    case AMCMC_MODEL_EIGHT_SCHOOLS: {
+      if (n_arrays != 2 || lens[0] != 8 || lens[1] != 8 || dim != 10) {
+        set_error("eight_schools: expects y[8], sigma[8], dim 10");
+        rc = AMCMC_ERR_ARG;
+        break;
+      }
+      double cst = std::log(5.0) + kLog2PiHalfH - (std::log(2.0) - std::log(M_PI) - std::log(5.0)) + 8 * kLog2PiHalfH;
+      for (int j = 0; j < 8; ++j) {
+        m->h_small[j] = arrays[0][j];
+        m->h_small[8 + j] = arrays[1][j];
+        if (!(arrays[1][j] > 0)) { set_error("eight_schools: sigma must be > 0"); rc = AMCMC_ERR_ARG; }
+        cst += std::log(arrays[1][j]) + kLog2PiHalfH;
+      }
+      m->cst = cst;
+      break;
+    }
+    case AMCMC_MODEL_KIDIQ: {
+      if (n_arrays != 3 || lens[0] < 1 || lens[1] != lens[0] || lens[2] != lens[0] || dim != 4) {
+        set_error("kidiq: expects kid_score[n], mom_hs[n], mom_iq[n], dim 4");
+        rc = AMCMC_ERR_ARG;
+        break;
+      }
+      m->n_rows = lens[0];
+      m->cst = -(std::log(2.0) - std::log(M_PI) - std::log(2.5)) + (double)m->n_rows * kLog2PiHalfH;
+      for (int k = 0; k < 3 && !rc; ++k) {
+        rc = upload(arrays[k], lens[k], dtype, &m->d_arr[k]);
+        m->arr_len[k] = lens[k];
+      }
+      break;
+    }
+    default:
+      set_error("model id %d not available in this build", model_id);
+      rc = AMCMC_ERR_UNSUPPORTED;
+  }
+  if (rc) { amcmc_model_destroy(m); return rc; }
+  *out = m;
+  return AMCMC_OK;
+}
+
+int amcmc_model_destroy(amcmc_model* m) {
+  if (!m) return AMCMC_OK;
+  for (int k = 0; k < 4; ++k)
+    if (m->d_arr[k]) cudaFree(m->d_arr[k]);
+  if (m->scratch) cudaFree(m->scratch);
+  free(m);
+  return AMCMC_OK;
+}
+
+int amcmc_model_dim(const amcmc_model* m) { return m ? m->dim : AMCMC_ERR_ARG; }
+int amcmc_model_dtype(const amcmc_model* m) { return m ? m->dtype : AMCMC_ERR_ARG; }
+
+static int validate_state(const amcmc_model* m, const amcmc_state* st, const char* who) {
+  if (!m || !st) { set_error("%s: NULL model/state", who); return AMCMC_ERR_ARG; }
+  if (st->dim != m->dim || st->dtype != m->dtype) {
+    set_error("%s: state (dim %d, dtype %d) does not match model (dim %d, dtype %d)", who, st->dim, st->dtype, m->dim, m->dtype);
+    return AMCMC_ERR_ARG;
+  }
+  if (st->n_chains < 1) { set_error("%s: n_chains must be >= 1", who); return AMCMC_ERR_ARG; }
+  if (!st->z || !st->potential_energy || !st->mean_accept_prob || !st->loc || !st->scale || !st->log_step_size || !st->as_change) {
+    set_error("%s: NULL state array", who);
+    return AMCMC_ERR_ARG;
+  }
+  return AMCMC_OK;
+}
+
+int amcmc_arwmh_init(const amcmc_model* m, amcmc_state* st, uint64_t seed, int64_t chain_offset, double init_radius,
+                     int use_given_z, void* stream) {
+  int rc = validate_state(m, st, "amcmc_arwmh_init");
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  st->i = 0;
+  switch (m->model_id) {
+    case AMCMC_MODEL_STD_NORMAL: return init_std_normal(m, st, seed, chain_offset, init_radius, use_given_z, s);
+    case AMCMC_MODEL_EIGHT_SCHOOLS: return init_eight_schools(m, st, seed, chain_offset, init_radius, use_given_z, s);
+    case AMCMC_MODEL_KIDIQ: return init_kidiq(m, st, seed, chain_offset, init_radius, use_given_z, s);
+  }
+  set_error("amcmc_arwmh_init: unsupported model %d", m->model_id);
+  return AMCMC_ERR_UNSUPPORTED;
+}
+
+static int validate_run(const amcmc_model* m, const amcmc_state* st, const amcmc_run_args* a) {
+  int rc = validate_state(m, st, "amcmc_arwmh_run");
+  if (rc) return rc;
+  if (!a) { set_error("amcmc_arwmh_run: NULL args"); return AMCMC_ERR_ARG; }
+  if (a->n_steps < 0 || a->thinning < 1 || a->collect_start < 0 || a->num_warmup < 0) {
+    set_error("amcmc_arwmh_run: need n_steps >= 0, thinning >= 1, collect_start >= 0, num_warmup >= 0");
+    return AMCMC_ERR_ARG;
+  }
+  if (a->rng_mode == AMCMC_RNG_EXTERNAL && a->n_steps > 0 && (!a->normals || !a->uniforms)) {
+    set_error("amcmc_arwmh_run: rng_mode EXTERNAL needs normals and uniforms");
+    return AMCMC_ERR_ARG;
+  }
+  if (a->rng_mode != AMCMC_RNG_EXTERNAL && a->rng_mode != AMCMC_RNG_PHILOX) {
+    set_error("amcmc_arwmh_run: bad rng_mode %d", a->rng_mode);
+    return AMCMC_ERR_ARG;
+  }
+  if (!(a->lr_decay >= 0) || !(a->eps >= 0)) { set_error("amcmc_arwmh_run: lr_decay/eps must be >= 0"); return AMCMC_ERR_ARG; }
+  return AMCMC_OK;
+}
+
+int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args* a, void* stream) {
+  int rc = validate_run(m, st, a);
+  if (rc) return rc;
+  if (a->n_steps == 0) return AMCMC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a->kernel_kind != AMCMC_KERNEL_ARWMH) {
+    set_error("amcmc_arwmh_run: kernel kind %d not available for model %d", a->kernel_kind, m->model_id);
+    return AMCMC_ERR_UNSUPPORTED;
+  }
+  switch (m->model_id) {
+    case AMCMC_MODEL_STD_NORMAL: rc = run_std_normal(m, st, a, s); break;
+    case AMCMC_MODEL_EIGHT_SCHOOLS: rc = run_eight_schools(m, st, a, s); break;
+    case AMCMC_MODEL_KIDIQ: rc = run_kidiq(m, st, a, s); break;
+    default:
+      set_error("amcmc_arwmh_run: unsupported model %d", m->model_id);
+      rc = AMCMC_ERR_UNSUPPORTED;
+  }
+  if (rc == AMCMC_OK) st->i += a->n_steps;
+  return rc;
+}
+
+int amcmc_potential(const amcmc_model* m, int64_t n, const void* q, void* out, void* stream) {
+  if (!m || !q || !out || n < 0) { set_error("amcmc_potential: bad argument"); return AMCMC_ERR_ARG; }
+  if (n == 0) return AMCMC_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (m->model_id) {
+    case AMCMC_MODEL_STD_NORMAL: return potential_std_normal(m, n, q, out, s);
+    case AMCMC_MODEL_EIGHT_SCHOOLS: return potential_eight_schools(m, n, q, out, s);
+    case AMCMC_MODEL_KIDIQ: return potential_kidiq(m, n, q, out, s);
+  }
+  set_error("amcmc_potential: unsupported model %d", m->model_id);
+  return AMCMC_ERR_UNSUPPORTED;
+}
+
+// Host-buffer variant: H2D state (+ draws), fused run, D2H state + samples.  Pointers in
+// *hst / *ha are host memory (pinned memory makes the copies truly asynchronous).
+int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args* ha) {
+  int rc = validate_run(m, hst, ha);
+  if (rc) return rc;
+  const size_t w = elt(m->dtype);
+  const int64_t C = hst->n_chains, d = hst->dim, T = ha->n_steps;
+  const int64_t np = d * (d + 1) / 2;
+  const int64_t S = (T > ha->collect_start) ? (T - ha->collect_start) / ha->thinning : 0;
+  const bool ext = ha->rng_mode == AMCMC_RNG_EXTERNAL;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_vec = al((size_t)C * w), b_mat = al((size_t)C * d * w), b_tri = al((size_t)C * np * w);
+  const size_t b_oz = ha->out_z ? al((size_t)S * d * C * w) : 0;
+  const size_t b_ope = ha->out_potential_energy ? al((size_t)S * C * w) : 0;
+  const size_t b_acc = ha->out_accept ? al((size_t)T * C) : 0;
+  const size_t b_nrm = ext ? al((size_t)T * d * C * w) : 0;
+  const size_t b_uni = ext ? al((size_t)T * C * w) : 0;
+  const size_t total = 4 * b_vec + 2 * b_mat + b_tri + b_oz + b_ope + b_acc + b_nrm + b_uni;
+  if (m->scratch_bytes < total) {
+    if (m->scratch) cudaFree(m->scratch);
+    m->scratch = nullptr;
+    m->scratch_bytes = 0;
+    rc = check_cuda(cudaMalloc(&m->scratch, total), "cudaMalloc(run_host scratch)");
+    if (rc) return rc;
+    m->scratch_bytes = total;
+  }
+  char* p = (char*)m->scratch;
+  auto take = [&](size_t b) { char* q = p; p += b; return (void*)q; };
+  amcmc_state ds = *hst;
+  ds.z = take(b_mat); ds.loc = take(b_mat); ds.scale = take(b_tri);
+  ds.potential_energy = take(b_vec); ds.mean_accept_prob = take(b_vec);
+  ds.log_step_size = take(b_vec); ds.as_change = take(b_vec);
+  amcmc_run_args da = *ha;
+  da.out_z = b_oz ? take(b_oz) : nullptr;
+  da.out_potential_energy = b_ope ? take(b_ope) : nullptr;
+  da.out_accept = b_acc ? (uint8_t*)take(b_acc) : nullptr;
+  da.normals = b_nrm ? take(b_nrm) : nullptr;
+  da.uniforms = b_uni ? take(b_uni) : nullptr;
+  cudaStream_t s = 0;
+#define H2D(dst, src, bytes) if ((rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s), "H2D"))) return rc
+#define D2H(dst, src, bytes) if ((rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s), "D2H"))) return rc
+  H2D(ds.z, hst->z, (size_t)C * d * w);
+  H2D(ds.loc, hst->loc, (size_t)C * d * w);
+  H2D(ds.scale, hst->scale, (size_t)C * np * w);
+  H2D(ds.potential_energy, hst->potential_energy, (size_t)C * w);
+  H2D(ds.mean_accept_prob, hst->mean_accept_prob, (size_t)C * w);
+  H2D(ds.log_step_size, hst->log_step_size, (size_t)C * w);
+  H2D(ds.as_change, hst->as_change, (size_t)C * w);
+  if (ext) {
+    H2D((void*)da.normals, ha->normals, (size_t)T * d * C * w);
+    H2D((void*)da.uniforms, ha->uniforms, (size_t)T * C * w);
+  }
+  rc = amcmc_arwmh_run(m, &ds, &da, (void*)s);
+  if (rc) return rc;
+  D2H(hst->z, ds.z, (size_t)C * d * w);
+  D2H(hst->loc, ds.loc, (size_t)C * d * w);
+  D2H(hst->scale, ds.scale, (size_t)C * np * w);
+  D2H(hst->potential_energy, ds.potential_energy, (size_t)C * w);
+  D2H(hst->mean_accept_prob, ds.mean_accept_prob, (size_t)C * w);
+  D2H(hst->log_step_size, ds.log_step_size, (size_t)C * w);
+  D2H(hst->as_change, ds.as_change, (size_t)C * w);
+  if (b_oz) D2H(ha->out_z, da.out_z, (size_t)S * d * C * w);
+  if (b_ope) D2H(ha->out_potential_energy, da.out_potential_energy, (size_t)S * C * w);
+  if (b_acc) D2H(ha->out_accept, da.out_accept, (size_t)T * C);
+#undef H2D
+#undef D2H
+  rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+  if (rc) return rc;
+  hst->i = ds.i;
+  return AMCMC_OK;
+}
+
+int amcmc_pooled_stats(const amcmc_state*, double*, void*) {
+  set_error("amcmc_pooled_stats: not available in this build");
+  return AMCMC_ERR_UNSUPPORTED;
+}
+
+int amcmc_pooled_set_adapt(amcmc_state*, const double*, const double*, double, int, void*) {
+  set_error("amcmc_pooled_set_adapt: not available in this build");
+  return AMCMC_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

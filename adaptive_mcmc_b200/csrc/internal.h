@@ -1,0 +1,41 @@
+// internal.h -- model handle and per-family launcher prototypes (not part of the public ABI).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/amcmc.h"
+
+struct amcmc_model {
+  int model_id;
+  int dtype;
+  int dim;
+  int device;
+  int64_t n_rows;        // data rows (kidiq, diamonds)
+  int n_arrays;
+  void* d_arr[4];        // device copies of the model arrays, converted to `dtype`
+  int64_t arr_len[4];
+  double h_small[32];    // small host-side constants (eight_schools y/sigma, folded constants)
+  double cst;            // folded additive constant of the potential
+  // diamonds / tensor-core path extras (filled by the family that needs them)
+  void* extra;           // family-private device/host block
+  // scratch for amcmc_arwmh_run_host
+  void* scratch;
+  size_t scratch_bytes;
+};
+
+namespace amcmc {
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+// Per-family entry points: run / init / potential.  Return amcmc_status.
+#define AMCMC_DECL_FAMILY(name)                                                                              \
+  int run_##name(const amcmc_model* m, const amcmc_state* st, const amcmc_run_args* a, cudaStream_t s);       \
+  int init_##name(const amcmc_model* m, const amcmc_state* st, uint64_t seed, int64_t chain_offset,           \
+                  double radius, int use_given_z, cudaStream_t s);                                            \
+  int potential_##name(const amcmc_model* m, int64_t n, const void* q, void* out, cudaStream_t s);
+
+AMCMC_DECL_FAMILY(std_normal)
+AMCMC_DECL_FAMILY(eight_schools)
+AMCMC_DECL_FAMILY(kidiq)
+
+}  // namespace amcmc

@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native many-chain adaptive Metropolis sampler.
+
+Metric (BASELINE.json): chain-steps/s (+ min-ESS/s) of the fused ARWMH step.  One bench "step"
+is ONE pass of the hot path over one batch: a fused launch of `--mcmc-steps` ARWMH iterations
+for `--chains` chains per GPU, with thinned sample collection.
+
+  python bench.py [--gpus N --steps K --warmup W]            # our arm
+  python bench.py --impl reference [...]                      # CPU arm (oracle port, all host cores)
+  torchrun --nproc-per-node N bench.py --gpus N ...           # N > 1 (chains shard, no data-path collective)
+
+Prints ONE JSON line (rank 0).  See the task contract in DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model, d, algorithmic HBM bytes per chain-step (2*w*(d(d+1)/2 + 2d + 3)), default chains)
+    "eight_schools": dict(d=10, bytes_per_step_f32=624, chains=65536,
+                          label="eight_schools_centered d=10, 65,536 independent chains per GPU (BASELINE.json configs[2])"),
+}
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="eight_schools", choices=sorted(WORKLOADS))
+    p.add_argument("--chains", type=int, default=None, help="chains per GPU")
+    p.add_argument("--mcmc-steps", type=int, default=1000, help="fused ARWMH iterations per bench step")
+    p.add_argument("--thinning", type=int, default=50, help="reference thins eight_schools by 50")
+    p.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference itself needs JAX + NumPyro, not installable here)
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(workload, dtype, chains, mcmc_steps, repeats=1, n_threads=0):
+    import numpy as np
+    from oracle import arwmh_numpy as onp, c_oracle
+
+    ndt = np.float32 if dtype == "f32" else np.float64
+    q0 = c_oracle.init_uniform(0, chains, 10, dt=ndt)
+    st = onp.arwmh_init(onp.make_potential("eight_schools"), q0)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        st, _ = c_oracle.arwmh_run(st, "eight_schools", mcmc_steps, seed=0, collect=False, n_threads=n_threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return chains * mcmc_steps / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    chains, T = 4096, 2000  # bounded sample: ~2 s of CPU work per bench step on 8 cores
+    import numpy as np
+    from oracle import arwmh_numpy as onp, c_oracle
+
+    ndt = np.float32 if args.dtype == "f32" else np.float64
+    q0 = c_oracle.init_uniform(0, chains, 10, dt=ndt)
+    st = onp.arwmh_init(onp.make_potential("eight_schools"), q0)
+    for _ in range(max(args.warmup, 1)):
+        st, _ = c_oracle.arwmh_run(st, "eight_schools", T, seed=0, thinning=args.thinning, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st, _ = c_oracle.arwmh_run(st, "eight_schools", T, seed=0, thinning=args.thinning, n_threads=cores)
+    el = time.perf_counter() - t0
+    val = chains * T * args.steps / el
+    sample = f"{chains} chains x {T} fused iterations per step (C oracle port, OpenMP over chains)"
+    line = {
+        "impl": "reference",
+        "metric": "chain-steps/sec",
+        "value": val,
+        "unit": "chain-steps/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": args.dtype,
+        "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload]["label"], "sample": sample, "thinning": args.thinning},
+        "cpu_baseline": {"value": val, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = JAX/NumPyro (not installable offline); timed arm is the C restatement oracle/arwmh_oracle.c",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
+            for ln in self.proc.stdout:
+                self.rows.append(ln.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import adaptive_mcmc_b200 as am
+    from adaptive_mcmc_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    Cn = args.chains or wl["chains"]
+    T = args.mcmc_steps
+    K, W = args.steps, max(args.warmup, 3)
+    tdt = torch.float32 if args.dtype == "f32" else torch.float64
+    esz = 4 if args.dtype == "f32" else 8
+    d = wl["d"]
+
+    # chains shard across ranks: global chain ids [rank*Cn, (rank+1)*Cn) -> no data-path collective
+    sampler = am.ARWMH(am.models.eight_schools, num_chains=Cn, dtype=tdt, device=dev, chain_offset=rank * Cn)
+    state = sampler.init(0, num_warmup=W * T, init_params=None)
+    batch = am.ChainBatch.from_state(sampler.potential, state, copy=False)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_step(collect=True):
+        return sampler.run_batch(batch, T, thinning=args.thinning, collect=("z", "potential_energy") if collect else ())
+
+    for _ in range(W):  # warm-up = the sampler's adaptation warm-up phase (W*T iterations)
+        one_step()
+    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kept = []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for k in range(K):
+        flush.fill_(k & 0xFF)  # L2 flush between timed iterations (not timed)
+        ev[k][0].record()
+        raw = one_step()
+        ev[k][1].record()
+        kept.append(raw["z"])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = K
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_max = float(tmax.item())
+    clk = clocks.stop() if rank == 0 else None
+
+    value = world * Cn * T * K / (ms_max * 1e-3)
+
+    # min-ESS/s over the timed (post-warm-up) region: NumPyro-definition ESS over all chains of this rank
+    zs = torch.cat(kept, dim=0).permute(2, 0, 1)  # [C, S, d]
+    sub = zs[: min(Cn, 8192)]
+    ess = am.diagnostics.effective_sample_size(sub)
+    min_ess = float(ess.min()) * (Cn / sub.shape[0]) * world
+    min_ess_per_s = min_ess / (ms_max * 1e-3)
+    acc = float(batch.macc.mean())
+
+    # ---- end-to-end through the C ABI with HOST buffers (H2D + run + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        host = {f: getattr(batch, f).cpu().pin_memory() for f in batch._FIELDS}
+        S = T // args.thinning
+        oz = torch.empty(S, d, Cn, dtype=tdt).pin_memory()
+        ope = torch.empty(S, Cn, dtype=tdt).pin_memory()
+        hs = _lib.AmcmcState()
+        hs.n_chains, hs.dim, hs.dtype, hs.i = Cn, d, (0 if args.dtype == "f32" else 1), batch.i
+        hs.z, hs.potential_energy, hs.mean_accept_prob = host["z"].data_ptr(), host["pe"].data_ptr(), host["macc"].data_ptr()
+        hs.loc, hs.scale, hs.log_step_size = host["loc"].data_ptr(), host["scale"].data_ptr(), host["lam"].data_ptr()
+        hs.as_change = host["asc"].data_ptr()
+        a = _lib.AmcmcRunArgs()
+        a.n_steps, a.thinning, a.collect_start, a.num_warmup = T, args.thinning, 0, W * T
+        a.lr_decay, a.target_accept_prob, a.eps = 2 / 3, 0.234, 1e-6
+        a.adapt, a.rng_mode, a.seed, a.chain_offset = 1, 0, 0, rank * Cn
+        a.out_z, a.out_potential_energy = oz.data_ptr(), ope.data_ptr()
+        h = sampler.potential.handle
+        L = _lib.lib()
+        for _ in range(2):
+            _lib.check(L.amcmc_arwmh_run_host(h, C.byref(hs), C.byref(a)), "run_host")
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            _lib.check(L.amcmc_arwmh_run_host(h, C.byref(hs), C.byref(a)), "run_host")
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        npk = d * (d + 1) // 2
+        state_bytes = Cn * esz * (2 * d + npk + 4)
+        e2e = {
+            "value": world * Cn * T * K / float(te.item()),
+            "unit": "chain-steps/s",
+            "h2d_bytes_per_step": state_bytes,
+            "d2h_bytes_per_step": state_bytes + S * (d + 1) * Cn * esz,
+            "api": "amcmc_arwmh_run_host (C ABI, pinned host buffers)",
+        }
+        launches += K
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bps = wl["bytes_per_step_f32"] * (esz // 4)
+    per_launch_s = (ms_max * 1e-3) / K
+    achieved = bps * Cn * T / per_launch_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{args.workload}_{args.dtype}")
+    line = {
+        "metric": "chain-steps/sec",
+        "value": value,
+        "unit": "chain-steps/s",
+        "n_gpus": world,
+        "steps": K,
+        "warmup": W,
+        "ms_per_step": ms_max / K,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": args.dtype,
+        "data": "synthetic",
+        "config": {
+            "workload": wl["label"],
+            "chains_per_gpu": Cn,
+            "fused_iterations_per_step": T,
+            "thinning": args.thinning,
+            "sampler": "ARWMH lr_decay=2/3 target=0.234 eps=1e-6, Philox4x32-10 in-kernel RNG",
+            "l2": "flushed between timed iterations (256 MiB fill)",
+            "parallelism": f"chains sharded over {world} GPU(s), no data-path collective",
+        },
+        "min_ess_per_sec": min_ess_per_s,
+        "mean_accept_prob": acc,
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {
+            "bound": "hbm",
+            "achieved": achieved,
+            "peak": hbm_peak,
+            "unit": "GB/s",
+            "frac": achieved / hbm_peak,
+            "traffic": traffic,
+            "note": ("algorithmic bytes = 2*w*(d(d+1)/2+2d+3) per chain-step (state round trip, SURVEY 8d) x chains x fused "
+                     "iterations per launch; peak = MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else
+                     "peak = fallback 6650 GB/s (of fallback)"),
+        },
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        cc, ct = 4096, 5000
+        rate, el = cpu_oracle_rate(args.workload, args.dtype, cc, ct, repeats=1, n_threads=cores)
+        line["cpu_baseline"] = {
+            "value": rate, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{cc} chains x {ct} iterations of the same workload, C oracle (oracle/arwmh_oracle.c), {el:.1f} s",
+        }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

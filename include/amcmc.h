@@ -1,0 +1,154 @@
+/* amcmc.h -- C ABI of libamcmc.so, the B200-native many-chain adaptive Metropolis sampler.
+ *
+ * This is the drop-in boundary for the hot path of savelovme/adaptive-mcmc:
+ * the ARWMH sampler kernel `python/kernels/arwmh.py` (class ARWMH, :31-276) plus
+ * the model log-densities it calls (`python/scripts/run_*_lr_decay.py`).  Every
+ * entry point below cites the reference interface it replaces (paths relative
+ * to the reference repo root).  Signatures use plain pointers and sizes only --
+ * no torch / C++ types -- so any FFI (ctypes, cffi, pybind, JAX custom_call) can
+ * bind them; INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - All state/draw/output pointers are DEVICE pointers on the current CUDA
+ *     device unless the function name ends in `_host`.
+ *   - Chain state is struct-of-arrays with the chain index fastest:
+ *       z[k*C + c], loc[k*C + c]                      k in [0,d)
+ *       scale[(i*(i+1)/2 + j)*C + c]                  packed lower triangle, j <= i
+ *     (the reference stores `scale` dense d x d with lower-triangular content,
+ *     arwmh.py:124; the Python host expands the packed form on request).
+ *   - dtype is AMCMC_F32 (reference precision) or AMCMC_F64 (parity path).
+ *   - Every function returns 0 on success, a negative amcmc_status otherwise,
+ *     never throws, and enqueues work on the caller's `stream` without a host
+ *     synchronisation (except `_host` variants, which synchronise before return).
+ */
+#ifndef AMCMC_H_
+#define AMCMC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMCMC_VERSION 100
+
+enum amcmc_dtype { AMCMC_F32 = 0, AMCMC_F64 = 1 };
+
+enum amcmc_status {
+  AMCMC_OK = 0,
+  AMCMC_ERR_ARG = -1,       /* bad argument (the reference raises ValueError, arwmh.py:69-70,118-119) */
+  AMCMC_ERR_CUDA = -2,      /* a CUDA runtime call failed; see amcmc_last_error() */
+  AMCMC_ERR_UNSUPPORTED = -3 /* model / dtype / dimension combination not compiled */
+};
+
+/* Model families = the NumPyro model functions the reference scripts define. */
+enum amcmc_model_id {
+  AMCMC_MODEL_STD_NORMAL = 0,   /* potential_fn = 0.5*|x|^2, python/jupyter/asumptions_check.ipynb cells 17-28 */
+  AMCMC_MODEL_EIGHT_SCHOOLS = 1, /* python/scripts/run_eight_schools_lr_decay.py:26-35 */
+  AMCMC_MODEL_KIDIQ = 2,        /* python/scripts/run_kidiq_kidscore_lr_decay.py:29-41 */
+  AMCMC_MODEL_DIAMONDS = 3,     /* python/scripts/run_diamonds_lr_decay.py:24-40 */
+  AMCMC_MODEL_GAUSSIAN = 4      /* BASELINE.json config 5: N(0, Sigma), precision Cholesky supplied */
+};
+
+enum amcmc_rng_mode {
+  AMCMC_RNG_PHILOX = 0,   /* in-kernel Philox4x32-10 keyed by (seed, global chain id, iteration) */
+  AMCMC_RNG_EXTERNAL = 1  /* caller supplies normals[T][d][C] and uniforms[T][C] (shared-draw parity mode) */
+};
+
+/* Sampler variants (arwmh.py is AMCMC_KERNEL_ARWMH; RAM is BASELINE.json config 5, not in the reference). */
+enum amcmc_kernel_kind { AMCMC_KERNEL_ARWMH = 0, AMCMC_KERNEL_RAM = 1 };
+
+typedef struct amcmc_model amcmc_model; /* opaque: device copies of the model data */
+
+/* Replaces numpyro.infer.util.initialize_model + potential_fn_gen(*args, **kwargs)
+ * (arwmh.py:111-116): binds model data and returns a handle whose potential the
+ * kernels inline.  `arrays` are HOST float64 arrays, copied to the current device:
+ *   STD_NORMAL    : none                          (dim = d)
+ *   EIGHT_SCHOOLS : y[8], sigma[8]                (dim = 10)
+ *   KIDIQ         : kid_score[n], mom_hs[n], mom_iq[n]   (dim = 4)
+ *   DIAMONDS      : X[n*K] row-major (col 0 = ones), Y[n]  (dim = K+1; lens[0] = n*K, lens[1] = n)
+ *   GAUSSIAN      : P[d*d] row-major lower Cholesky of the precision  (dim = d)
+ */
+int amcmc_model_create(amcmc_model** out, int model_id, int dtype, int dim, int n_arrays,
+                       const double* const* arrays, const int64_t* lens);
+int amcmc_model_destroy(amcmc_model* m);
+int amcmc_model_dim(const amcmc_model* m);
+int amcmc_model_dtype(const amcmc_model* m);
+
+/* ARWMHState + ARWMHAdaptState (arwmh.py:15-28) for C chains, as device SoA pointers. */
+typedef struct amcmc_state {
+  int64_t n_chains;        /* C */
+  int32_t dim;             /* d */
+  int32_t dtype;           /* amcmc_dtype */
+  int64_t i;               /* ARWMHState.i  -- shared by all chains; advanced by run */
+  void* z;                 /* ARWMHState.z (flat, ravel_pytree order)  [d][C] */
+  void* potential_energy;  /* [C] */
+  void* mean_accept_prob;  /* [C] */
+  void* loc;               /* ARWMHAdaptState.loc            [d][C] */
+  void* scale;             /* ARWMHAdaptState.scale, packed  [d(d+1)/2][C] */
+  void* log_step_size;     /* ARWMHAdaptState.log_step_size  [C] */
+  void* as_change;         /* [C] */
+} amcmc_state;
+
+/* ARWMH.__init__ hyper-parameters (arwmh.py:43-45) + ARWMH.init's num_warmup (:107)
+ * + the driver's collection plan (numpyro.util.fori_collect as used at
+ * python/utils/kernel_utils.py:29-32: sample k = state after
+ * collect_start + (k+1)*thinning steps). */
+typedef struct amcmc_run_args {
+  int64_t n_steps;         /* K fused steps in this call */
+  int64_t thinning;        /* >= 1 */
+  int64_t collect_start;   /* steps to skip before collection starts */
+  int64_t num_warmup;      /* arwmh.py:181: n restarts at 1 after warmup */
+  double lr_decay;         /* gamma = n^-lr_decay (arwmh.py:183) */
+  double target_accept_prob;
+  double eps;              /* proposal regularisation (arwmh.py:166) */
+  int32_t adapt;           /* 1: ARWMH.sample (:140-207); 0: frozen kernel of sample_Pnx (:230-249) */
+  int32_t rng_mode;        /* amcmc_rng_mode */
+  uint64_t seed;
+  int64_t chain_offset;    /* global id of this shard's first chain (multi-GPU sharding) */
+  const void* normals;     /* EXTERNAL: [n_steps][d][C] */
+  const void* uniforms;    /* EXTERNAL: [n_steps][C] */
+  void* out_z;             /* [S][d][C] or NULL, S = (n_steps - collect_start) / thinning */
+  void* out_potential_energy; /* [S][C] or NULL */
+  uint8_t* out_accept;     /* [n_steps][C] accept decisions, or NULL (parity tests) */
+  int32_t kernel_kind;     /* amcmc_kernel_kind */
+  int32_t impl;            /* 0 = auto; 1 = thread-per-chain registers; 2 = block-per-chain smem; 3 = tcgen05 */
+} amcmc_run_args;
+
+/* ARWMH.init (arwmh.py:84-138).  If use_given_z == 0 draws q0 ~ U(-init_radius, init_radius)^d
+ * per chain (NumPyro init_to_uniform, radius 2) from the Philox stream; otherwise keeps
+ * state->z.  Then U0 = potential(q0); loc = q0; scale = I; log_step_size = 0;
+ * mean_accept_prob = 0; as_change = 0; i = 0. */
+int amcmc_arwmh_init(const amcmc_model* m, amcmc_state* state, uint64_t seed, int64_t chain_offset,
+                     double init_radius, int use_given_z, void* stream);
+
+/* ARWMH.sample (arwmh.py:140-207) fused over args->n_steps steps for all chains,
+ * with fori_collect-style thinned collection.  Updates *state in place (state->i too). */
+int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* state, const amcmc_run_args* args, void* stream);
+
+/* potential_fn(z) (arwmh.py:121,170) for n points, q laid out [d][n]. */
+int amcmc_potential(const amcmc_model* m, int64_t n, const void* q, void* out, void* stream);
+
+/* Same as amcmc_arwmh_run but every pointer in *state and the out_* / normals /
+ * uniforms pointers in *args are HOST buffers: state is copied to the device,
+ * the fused steps run, and state + collected samples are copied back before
+ * returning (this is what a non-CUDA caller, e.g. the reference's NumPy/JAX-CPU
+ * scripts, would bind).  Device scratch is cached inside the model handle. */
+int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* host_state, const amcmc_run_args* host_args);
+
+/* Pooled-adaptation support (BASELINE.json config 4; not in the reference):
+ * per-shard sufficient statistics of the current positions, out = [1 + d + d(d+1)/2]
+ * float64 on device: (count, sum x_k, sum x_i x_j for j <= i).  The caller
+ * all-reduces them (NCCL) and calls amcmc_pooled_set_scale. */
+int amcmc_pooled_stats(const amcmc_state* state, double* out_stats, void* stream);
+/* Broadcast one (loc[d], packed scale[d(d+1)/2], log_step_size) to all chains of the shard. */
+int amcmc_pooled_set_adapt(amcmc_state* state, const double* loc, const double* scale_packed,
+                           double log_step_size, int set_log_step, void* stream);
+
+const char* amcmc_last_error(void);
+int amcmc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMCMC_H_ */

@@ -1,0 +1,222 @@
+"""GPU parity tests for the thread-per-chain fused kernel (eight_schools, kidiq, std_normal):
+the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances (north star): identical accept/reject decisions and trajectories within 1e-5 relative
+in fp64 and 1e-3 in fp32, over T = 300 steps.  fp32 chains whose accept sequence flips because
+|u - alpha| fell inside rounding error are compared only up to the flip, and at most 10 % of the
+chains may flip."""
+import numpy as np
+import pytest
+import torch
+
+import adaptive_mcmc_b200 as am
+from adaptive_mcmc_b200 import models
+from oracle import arwmh_numpy as o
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f64": (torch.float64, np.float64, 1e-5), "f32": (torch.float32, np.float32, 1e-3)}
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _oracle_state(state, ndt):
+    zf = np.concatenate([_np(v).reshape(_np(v).shape[0], -1) for v in state.z.values()], axis=1).astype(ndt)
+    a = state.adapt_state
+    return o.ARWMHState(int(state.i), zf, _np(state.potential_energy).astype(ndt), _np(state.mean_accept_prob).astype(ndt),
+                        o.ARWMHAdaptState(_np(a.loc).astype(ndt), _np(a.scale).astype(ndt), _np(a.log_step_size).astype(ndt)),
+                        _np(state.as_change).astype(ndt), 0)
+
+
+def _flat(zdict):
+    return np.concatenate([_np(v).reshape(*_np(v).shape[:2], -1) for v in zdict.values()], axis=-1)
+
+
+def _compare(coll, last, ocoll, olast, tol, min_same):
+    acc_g, acc_o = _np(coll["accept"]), ocoll["accepts"]
+    same = (acc_g == acc_o).all(axis=0)
+    assert same.mean() >= min_same, f"only {same.mean():.3f} of chains keep identical accept decisions"
+    zg, zo = _flat(coll["z"]), ocoll["z"]
+    assert zg.shape == zo.shape
+    scale = 1.0 + np.abs(zo)
+    assert (np.abs(zg - zo) / scale)[:, same].max() < tol
+    # chains that flipped agree up to (not including) the flip
+    T = acc_g.shape[0]
+    for c in np.nonzero(~same)[0]:
+        t_flip = int(np.argmax(acc_g[:, c] != acc_o[:, c]))
+        if zg.shape[0] == T and t_flip > 0:
+            assert (np.abs(zg[:t_flip, c] - zo[:t_flip, c]) / scale[:t_flip, c]).max() < tol
+    a, oa = last.adapt_state, olast.adapt_state
+    for g, r in ((a.loc, oa.loc), (a.scale, oa.scale), (a.log_step_size, oa.log_step_size),
+                 (last.potential_energy, olast.potential_energy), (last.mean_accept_prob, olast.mean_accept_prob),
+                 (last.as_change, olast.as_change)):
+        g, r = _np(g)[same], r[same]
+        assert (np.abs(g - r) / (1.0 + np.abs(r))).max() < tol
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("kw", [dict(), dict(num_warmup=100, lr_decay=0.5), dict(lr_decay=1.0, target_accept_prob=0.3, eps=1e-3)])
+def test_eight_schools_shared_draws(prec, kw):
+    tdt, ndt, tol = DT[prec]
+    C, T, d = 512, 300, 10
+    nw = kw.pop("num_warmup", 0)
+    sampler = am.ARWMH(models.eight_schools, num_chains=C, dtype=tdt, **kw)
+    state = sampler.init(42, num_warmup=nw, init_params=None)
+    ost = _oracle_state(state, ndt)
+    # init: q0 ~ U(-2,2), U0, loc = q0, scale = I  (arwmh.py:111-136)
+    np.testing.assert_array_equal(ost.z, co.init_uniform(42, C, d, dt=ndt))
+    np.testing.assert_allclose(ost.potential_energy, o.potential_eight_schools(ost.z.astype(np.float64)), rtol=10 * tol)
+    np.testing.assert_array_equal(ost.adapt_state.scale, np.broadcast_to(np.eye(d, dtype=ndt), (C, d, d)))
+    rng = np.random.default_rng(7)
+    nrm = rng.normal(size=(T, C, d)).astype(ndt)
+    uni = rng.random(size=(T, C)).astype(ndt)
+    coll, last = sampler.run(state, T, draws=(torch.from_numpy(nrm), torch.from_numpy(uni)), record_accept=True)
+    okw = dict(num_warmup=nw, lr_decay=kw.get("lr_decay", 2 / 3), target_accept_prob=kw.get("target_accept_prob", 0.234),
+               eps=kw.get("eps", 1e-6))
+    olast, ocoll = co.arwmh_run(ost, "eight_schools", T, draws=(nrm, uni), record_accept=True, **okw)
+    assert int(last.i) == T
+    _compare(coll, last, ocoll, olast, tol, 1.0 if prec == "f64" else 0.9)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_eight_schools_philox_stream_matches_oracle(prec):
+    tdt, ndt, tol = DT[prec]
+    C, T = 256, 200
+    sampler = am.ARWMH(models.eight_schools, num_chains=C, dtype=tdt, chain_offset=1000)
+    state = sampler.init(5, num_warmup=50, init_params=None)
+    ost = _oracle_state(state, ndt)
+    coll, last = sampler.run(state, T, thinning=4, collect_start=50, record_accept=True)
+    olast, ocoll = co.arwmh_run(ost, "eight_schools", T, seed=5, chain_offset=1000, thinning=4, collect_start=50,
+                                num_warmup=50, record_accept=True)
+    # the device draws its normals with SFU log/sin/cos: allow the looser fp32 tolerance in both precisions
+    _compare(coll, last, ocoll, olast, max(tol, 1e-3), 0.9)
+    assert coll["z"]["mu"].shape == ((T - 50) // 4, C)
+
+
+def test_thinning_segmentation_and_single_step_protocol():
+    C = 128
+    sampler = am.ARWMH(models.eight_schools, num_chains=C, dtype=torch.float64)
+    s0 = sampler.init(9, num_warmup=0, init_params=None)
+    coll, full = sampler.run(s0, 60, thinning=5)
+    s = s0
+    for k in (1, 1, 18, 40):  # same stream cut into 4 launches; `sample` is the K=1 protocol call
+        s = sampler.sample(s) if k == 1 else sampler.run(s, k, collect=())[1]
+    assert int(s.i) == 60 and int(s0.i) == 0  # functional: the input state is untouched
+    np.testing.assert_allclose(_np(s.adapt_state.scale), _np(full.adapt_state.scale), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(_flat({k: v[None] for k, v in s.z.items()})[0], _flat({k: v[None] for k, v in full.z.items()})[0], rtol=1e-9)
+    np.testing.assert_allclose(_np(s.as_change), _np(full.as_change), rtol=1e-8)
+    assert coll["potential_energy"].shape == (12, C)
+    np.testing.assert_allclose(_np(coll["potential_energy"][-1]), _np(full.potential_energy), rtol=1e-12)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_kidiq_shared_draws(prec):
+    tdt, ndt, tol = DT[prec]
+    data = models.synthetic_kidiq()
+    C, T, d = 128, 200, 4
+    sampler = am.ARWMH(models.kidiq, num_chains=C, dtype=tdt)
+    state = sampler.init(3, num_warmup=0, init_params=None, model_kwargs=data)
+    ost = _oracle_state(state, ndt)
+    np.testing.assert_allclose(ost.potential_energy, o.potential_kidiq(ost.z.astype(np.float64), **data), rtol=10 * tol)
+    rng = np.random.default_rng(8)
+    nrm = rng.normal(size=(T, C, d)).astype(ndt)
+    uni = rng.random(size=(T, C)).astype(ndt)
+    coll, last = sampler.run(state, T, draws=(torch.from_numpy(nrm), torch.from_numpy(uni)), record_accept=True)
+    olast, ocoll = co.arwmh_run(ost, "kidiq", T, draws=(nrm, uni), record_accept=True, **data)
+    _compare(coll, last, ocoll, olast, tol if prec == "f64" else 5e-3, 1.0 if prec == "f64" else 0.8)
+
+
+def test_potential_entry_point_and_potential_fn_mode():
+    pot = models.eight_schools.bind(dtype=torch.float64)
+    rng = np.random.default_rng(0)
+    q = rng.normal(size=(1000, 10))
+    np.testing.assert_allclose(_np(pot(torch.from_numpy(q))), o.potential_eight_schools(q), rtol=1e-12)
+    # potential_fn mode requires init_params (arwmh.py:118-119)
+    s = am.ARWMH(potential_fn=pot)
+    with pytest.raises(ValueError):
+        s.init(0, 0, None, (), {})
+    st = s.init(0, 0, {"mu": torch.zeros(3), "tau": torch.zeros(3), "theta_base": torch.zeros(3, 8)}, (), {})
+    np.testing.assert_allclose(_np(st.potential_energy), 43.43563727714813, rtol=1e-12)
+    assert "Acceptance rate: 0.00, Step size: 1.000" == s.get_diagnostics_str(st)
+
+
+def test_sample_Pnx_frozen_kernel_invariance():
+    # asumptions_check.ipynb cells 27-28: exact N(0,1) draws pushed through P stay N(0,1)
+    pot = models.std_normal.bind(d=1, dtype=torch.float32)
+    s = am.ARWMH(potential_fn=pot)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(200000, 1, generator=g)
+    adapt = am.ARWMHAdaptState(torch.zeros(1), torch.eye(1), torch.tensor(0.3))
+    out = s.sample_Pnx(3, x, adapt, n=3, n_samples=2)
+    assert out.shape == (200000, 2, 1)
+    y = out.reshape(-1).double().cpu()
+    assert abs(float(y.mean())) < 0.01 and abs(float(y.std()) - 1.0) < 0.01
+    from scipy import stats
+    assert stats.kstest(y.numpy()[::4], "norm").pvalue > 1e-3
+    # frozen: a chain that moves changes x but never the adaptation state; n steps of P from one point
+    out2 = s.sample_Pnx(3, torch.zeros(1, 1), adapt, n=50, n_samples=50000)
+    y2 = out2.reshape(-1).double().cpu()
+    assert abs(float(y2.std()) - 1.0) < 0.03
+
+
+def test_mcmc_driver_posterior_matches_reference_table():
+    import json, os
+    tab = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_pins.json")))["eight_schools_arwmh_table"]
+    mcmc = am.MCMC(am.ARWMH(models.eight_schools), num_warmup=5000, num_samples=20000, thinning=20, num_chains=2048)
+    mcmc.run(0, sigma=models.eight_schools.SIGMA, y=models.eight_schools.Y, extra_fields=("potential_energy",))
+    samples = mcmc.get_samples(group_by_chain=True)
+    assert set(samples) == {"mu", "tau", "theta", "theta_base"} and samples["theta"].shape == (2048, 1000, 8)
+    flat = mcmc.get_samples()
+    assert flat["mu"].shape == (2048 * 1000,)
+    mean = np.array([float(flat["mu"].mean())] + [float(v) for v in flat["theta_base"].mean(0)])
+    std = np.array([float(flat["mu"].std())] + [float(v) for v in flat["theta_base"].std(0)])
+    idx = [0] + list(range(2, 10))
+    np.testing.assert_allclose(mean, np.array(tab["mean"])[idx], atol=0.06)
+    np.testing.assert_allclose(std, np.array(tab["std"])[idx], atol=0.06)
+    pe = mcmc.get_extra_fields()["potential_energy"]
+    assert float(pe.min()) > 40.05
+    acc = float(mcmc.last_state.mean_accept_prob.mean())
+    assert 0.2 < acc < 0.27
+    summ = am.diagnostics.summary({"mu": samples["mu"][:64]})
+    assert float(summ["mu"]["r_hat"]) < 1.05
+
+
+def test_mcmc_extra_adapt_state_and_logscale_collection():
+    mcmc = am.MCMC(am.ARWMH(models.eight_schools, dtype=torch.float64), num_warmup=20, num_samples=30, thinning=10, num_chains=8)
+    mcmc.run(1, extra_fields=("potential_energy", "adapt_state"))
+    ex = mcmc.get_extra_fields(group_by_chain=True)
+    assert ex["adapt_state"].scale.shape == (8, 3, 10, 10) and ex["adapt_state"].loc.shape == (8, 3, 10)
+    # identical chain whether collected in one fused launch or per-sample launches
+    m2 = am.MCMC(am.ARWMH(models.eight_schools, dtype=torch.float64), num_warmup=20, num_samples=30, thinning=10, num_chains=8)
+    m2.run(1, extra_fields=("potential_energy",))
+    np.testing.assert_allclose(_np(ex["potential_energy"]), _np(m2.get_extra_fields(group_by_chain=True)["potential_energy"]), rtol=1e-9)
+    states = am.collect_states_logscale(2, am.ARWMH(models.eight_schools, num_chains=4), {}, n_pow=3)
+    n = len(am.ns_logscale(3))
+    assert states.potential_energy.shape == (n, 4) and states.adapt_state.scale.shape == (n, 4, 10, 10)
+    np.testing.assert_array_equal(states.i.numpy(), am.ns_logscale(3).numpy())
+    assert float(states.as_change[-1].max()) < float(states.as_change[1].max())  # adaptation decays
+
+
+def test_run_host_entry_point_matches_device_path():
+    import ctypes as C
+    from adaptive_mcmc_b200 import _lib
+    Cn, T = 256, 40
+    sampler = am.ARWMH(models.eight_schools, num_chains=Cn)
+    st = sampler.init(4, num_warmup=0, init_params=None)
+    b = am.ChainBatch.from_state(sampler.potential, st)
+    host = {f: getattr(b, f).cpu().pin_memory() for f in b._FIELDS}
+    raw = sampler.run_batch(b, T, thinning=2)
+    hs = _lib.AmcmcState(); hs.n_chains = Cn; hs.dim = 10; hs.dtype = 0; hs.i = 0
+    hs.z = host["z"].data_ptr(); hs.potential_energy = host["pe"].data_ptr(); hs.mean_accept_prob = host["macc"].data_ptr()
+    hs.loc = host["loc"].data_ptr(); hs.scale = host["scale"].data_ptr(); hs.log_step_size = host["lam"].data_ptr()
+    hs.as_change = host["asc"].data_ptr()
+    a = _lib.AmcmcRunArgs(); a.n_steps = T; a.thinning = 2; a.lr_decay = 2 / 3; a.target_accept_prob = 0.234; a.eps = 1e-6
+    a.adapt = 1; a.rng_mode = 0; a.seed = 4
+    oz = torch.empty(T // 2, 10, Cn).pin_memory(); a.out_z = oz.data_ptr()
+    _lib.check(_lib.lib().amcmc_arwmh_run_host(sampler.potential.handle, C.byref(hs), C.byref(a)), "run_host")
+    assert hs.i == T
+    torch.testing.assert_close(oz, raw["z"].cpu(), rtol=0, atol=0)
+    torch.testing.assert_close(host["scale"], b.scale.cpu(), rtol=0, atol=0)
