@@ -100,6 +100,15 @@ int amcmc_model_create(amcmc_model** out, int model_id, int dtype, int dim, int 
       }
       break;
     }
+    case AMCMC_MODEL_DIAMONDS: {
+      if (n_arrays != 2 || lens[1] < 1 || lens[0] % lens[1] != 0 || lens[0] / lens[1] != dim - 1 || dim < 3 || dim > 32) {
+        set_error("diamonds: expects X[n*K] (row-major, column 0 = ones), Y[n], dim = K + 1 <= 32");
+        rc = AMCMC_ERR_ARG;
+        break;
+      }
+      rc = create_diamonds(m, arrays[0], lens[1], dim - 1, arrays[1]);
+      break;
+    }
     default:
       set_error("model id %d not available in this build", model_id);
       rc = AMCMC_ERR_UNSUPPORTED;
@@ -114,6 +123,10 @@ int amcmc_model_destroy(amcmc_model* m) {
   for (int k = 0; k < 4; ++k)
     if (m->d_arr[k]) cudaFree(m->d_arr[k]);
   if (m->scratch) cudaFree(m->scratch);
+  if (m->host_streams_ready) {
+    for (int k = 0; k < 2; ++k) cudaStreamDestroy(m->host_streams[k]);
+    for (int k = 0; k < 4; ++k) cudaEventDestroy(m->host_events[k]);
+  }
   free(m);
   return AMCMC_OK;
 }
@@ -145,6 +158,7 @@ int amcmc_arwmh_init(const amcmc_model* m, amcmc_state* st, uint64_t seed, int64
     case AMCMC_MODEL_STD_NORMAL: return init_std_normal(m, st, seed, chain_offset, init_radius, use_given_z, s);
     case AMCMC_MODEL_EIGHT_SCHOOLS: return init_eight_schools(m, st, seed, chain_offset, init_radius, use_given_z, s);
     case AMCMC_MODEL_KIDIQ: return init_kidiq(m, st, seed, chain_offset, init_radius, use_given_z, s);
+    case AMCMC_MODEL_DIAMONDS: return init_diamonds(m, st, seed, chain_offset, init_radius, use_given_z, s);
   }
   set_error("amcmc_arwmh_init: unsupported model %d", m->model_id);
   return AMCMC_ERR_UNSUPPORTED;
@@ -183,6 +197,7 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
     case AMCMC_MODEL_STD_NORMAL: rc = run_std_normal(m, st, a, s); break;
     case AMCMC_MODEL_EIGHT_SCHOOLS: rc = run_eight_schools(m, st, a, s); break;
     case AMCMC_MODEL_KIDIQ: rc = run_kidiq(m, st, a, s); break;
+    case AMCMC_MODEL_DIAMONDS: rc = run_diamonds_block(m, st, a, s); break;
     default:
       set_error("amcmc_arwmh_run: unsupported model %d", m->model_id);
       rc = AMCMC_ERR_UNSUPPORTED;
@@ -199,29 +214,37 @@ int amcmc_potential(const amcmc_model* m, int64_t n, const void* q, void* out, v
     case AMCMC_MODEL_STD_NORMAL: return potential_std_normal(m, n, q, out, s);
     case AMCMC_MODEL_EIGHT_SCHOOLS: return potential_eight_schools(m, n, q, out, s);
     case AMCMC_MODEL_KIDIQ: return potential_kidiq(m, n, q, out, s);
+    case AMCMC_MODEL_DIAMONDS: return potential_diamonds_block(m, n, q, out, s);
   }
   set_error("amcmc_potential: unsupported model %d", m->model_id);
   return AMCMC_ERR_UNSUPPORTED;
 }
 
 // Host-buffer variant: H2D state (+ draws), fused run, D2H state + samples.  Pointers in
-// *hst / *ha are host memory (pinned memory makes the copies truly asynchronous).
+// *hst / *ha are host memory (pinned memory makes the copies truly asynchronous).  The run is cut
+// into chunks of whole thinning periods; chunk k's samples travel device->host on a second stream
+// while chunk k+1 computes, so the PCIe/C2C copy of the sample stream hides behind the kernel.
 int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args* ha) {
   int rc = validate_run(m, hst, ha);
   if (rc) return rc;
   const size_t w = elt(m->dtype);
   const int64_t C = hst->n_chains, d = hst->dim, T = ha->n_steps;
   const int64_t np = d * (d + 1) / 2;
-  const int64_t S = (T > ha->collect_start) ? (T - ha->collect_start) / ha->thinning : 0;
+  const int64_t thin = ha->thinning;
+  const int64_t S = (T > ha->collect_start) ? (T - ha->collect_start) / thin : 0;
   const bool ext = ha->rng_mode == AMCMC_RNG_EXTERNAL;
+  const bool want_z = ha->out_z && S > 0, want_pe = ha->out_potential_energy && S > 0;
+  // chunking: ~2048 iterations per chunk, whole thinning periods, at most S samples
+  int64_t chunk_S = (want_z || want_pe) ? ((2048 + thin - 1) / thin) : 0;
+  if (chunk_S > S) chunk_S = S;
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t b_vec = al((size_t)C * w), b_mat = al((size_t)C * d * w), b_tri = al((size_t)C * np * w);
-  const size_t b_oz = ha->out_z ? al((size_t)S * d * C * w) : 0;
-  const size_t b_ope = ha->out_potential_energy ? al((size_t)S * C * w) : 0;
+  const size_t b_oz = want_z ? al((size_t)chunk_S * d * C * w) : 0;
+  const size_t b_ope = want_pe ? al((size_t)chunk_S * C * w) : 0;
   const size_t b_acc = ha->out_accept ? al((size_t)T * C) : 0;
   const size_t b_nrm = ext ? al((size_t)T * d * C * w) : 0;
   const size_t b_uni = ext ? al((size_t)T * C * w) : 0;
-  const size_t total = 4 * b_vec + 2 * b_mat + b_tri + b_oz + b_ope + b_acc + b_nrm + b_uni;
+  const size_t total = 4 * b_vec + 2 * b_mat + b_tri + 2 * (b_oz + b_ope) + b_acc + b_nrm + b_uni;
   if (m->scratch_bytes < total) {
     if (m->scratch) cudaFree(m->scratch);
     m->scratch = nullptr;
@@ -230,21 +253,27 @@ int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args*
     if (rc) return rc;
     m->scratch_bytes = total;
   }
+  if (!m->host_streams_ready) {
+    for (int k = 0; k < 2; ++k)
+      if ((rc = check_cuda(cudaStreamCreateWithFlags(&m->host_streams[k], cudaStreamNonBlocking), "cudaStreamCreate"))) return rc;
+    for (int k = 0; k < 4; ++k)
+      if ((rc = check_cuda(cudaEventCreateWithFlags(&m->host_events[k], cudaEventDisableTiming), "cudaEventCreate"))) return rc;
+    m->host_streams_ready = 1;
+  }
+  cudaStream_t s0 = m->host_streams[0], s1 = m->host_streams[1];
   char* p = (char*)m->scratch;
   auto take = [&](size_t b) { char* q = p; p += b; return (void*)q; };
   amcmc_state ds = *hst;
   ds.z = take(b_mat); ds.loc = take(b_mat); ds.scale = take(b_tri);
   ds.potential_energy = take(b_vec); ds.mean_accept_prob = take(b_vec);
   ds.log_step_size = take(b_vec); ds.as_change = take(b_vec);
-  amcmc_run_args da = *ha;
-  da.out_z = b_oz ? take(b_oz) : nullptr;
-  da.out_potential_energy = b_ope ? take(b_ope) : nullptr;
-  da.out_accept = b_acc ? (uint8_t*)take(b_acc) : nullptr;
-  da.normals = b_nrm ? take(b_nrm) : nullptr;
-  da.uniforms = b_uni ? take(b_uni) : nullptr;
-  cudaStream_t s = 0;
-#define H2D(dst, src, bytes) if ((rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s), "H2D"))) return rc
-#define D2H(dst, src, bytes) if ((rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s), "D2H"))) return rc
+  void* d_oz[2] = {b_oz ? take(b_oz) : nullptr, b_oz ? take(b_oz) : nullptr};
+  void* d_ope[2] = {b_ope ? take(b_ope) : nullptr, b_ope ? take(b_ope) : nullptr};
+  uint8_t* d_acc = b_acc ? (uint8_t*)take(b_acc) : nullptr;
+  void* d_nrm = b_nrm ? take(b_nrm) : nullptr;
+  void* d_uni = b_uni ? take(b_uni) : nullptr;
+#define H2D(dst, src, bytes) if ((rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s0), "H2D"))) return rc
+#define D2H(dst, src, bytes, st) if ((rc = check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st), "D2H"))) return rc
   H2D(ds.z, hst->z, (size_t)C * d * w);
   H2D(ds.loc, hst->loc, (size_t)C * d * w);
   H2D(ds.scale, hst->scale, (size_t)C * np * w);
@@ -253,25 +282,59 @@ int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args*
   H2D(ds.log_step_size, hst->log_step_size, (size_t)C * w);
   H2D(ds.as_change, hst->as_change, (size_t)C * w);
   if (ext) {
-    H2D((void*)da.normals, ha->normals, (size_t)T * d * C * w);
-    H2D((void*)da.uniforms, ha->uniforms, (size_t)T * C * w);
+    H2D(d_nrm, ha->normals, (size_t)T * d * C * w);
+    H2D(d_uni, ha->uniforms, (size_t)T * C * w);
   }
-  rc = amcmc_arwmh_run(m, &ds, &da, (void*)s);
-  if (rc) return rc;
-  D2H(hst->z, ds.z, (size_t)C * d * w);
-  D2H(hst->loc, ds.loc, (size_t)C * d * w);
-  D2H(hst->scale, ds.scale, (size_t)C * np * w);
-  D2H(hst->potential_energy, ds.potential_energy, (size_t)C * w);
-  D2H(hst->mean_accept_prob, ds.mean_accept_prob, (size_t)C * w);
-  D2H(hst->log_step_size, ds.log_step_size, (size_t)C * w);
-  D2H(hst->as_change, ds.as_change, (size_t)C * w);
-  if (b_oz) D2H(ha->out_z, da.out_z, (size_t)S * d * C * w);
-  if (b_ope) D2H(ha->out_potential_energy, da.out_potential_energy, (size_t)S * C * w);
-  if (b_acc) D2H(ha->out_accept, da.out_accept, (size_t)T * C);
+  int64_t t_done = 0, s_done = 0;
+  int k = 0;
+  while (t_done < T) {
+    amcmc_run_args da = *ha;
+    int64_t steps, ns;
+    if (chunk_S > 0 && s_done < S) {
+      ns = (S - s_done < chunk_S) ? (S - s_done) : chunk_S;
+      da.collect_start = (t_done == 0) ? ha->collect_start : 0;
+      steps = da.collect_start + ns * thin;
+      if (s_done + ns == S) steps = T - t_done;  // the last chunk also takes the uncollected tail
+    } else {
+      ns = 0;
+      steps = T - t_done;
+      da.collect_start = steps;  // nothing left to collect
+    }
+    da.n_steps = steps;
+    const int buf = k & 1;
+    if (k >= 2) {  // buffer reuse: wait until its previous copy has drained
+      if ((rc = check_cuda(cudaStreamWaitEvent(s0, m->host_events[2 + buf], 0), "cudaStreamWaitEvent"))) return rc;
+    }
+    da.out_z = (want_z && ns) ? d_oz[buf] : nullptr;
+    da.out_potential_energy = (want_pe && ns) ? d_ope[buf] : nullptr;
+    da.out_accept = d_acc ? d_acc + (size_t)t_done * C : nullptr;
+    da.normals = ext ? (const void*)((const char*)d_nrm + (size_t)t_done * d * C * w) : nullptr;
+    da.uniforms = ext ? (const void*)((const char*)d_uni + (size_t)t_done * C * w) : nullptr;
+    rc = amcmc_arwmh_run(m, &ds, &da, (void*)s0);
+    if (rc) return rc;
+    if (ns && (want_z || want_pe)) {
+      if ((rc = check_cuda(cudaEventRecord(m->host_events[buf], s0), "cudaEventRecord"))) return rc;
+      if ((rc = check_cuda(cudaStreamWaitEvent(s1, m->host_events[buf], 0), "cudaStreamWaitEvent"))) return rc;
+      if (want_z) D2H((char*)ha->out_z + (size_t)s_done * d * C * w, d_oz[buf], (size_t)ns * d * C * w, s1);
+      if (want_pe) D2H((char*)ha->out_potential_energy + (size_t)s_done * C * w, d_ope[buf], (size_t)ns * C * w, s1);
+      if ((rc = check_cuda(cudaEventRecord(m->host_events[2 + buf], s1), "cudaEventRecord"))) return rc;
+      ++k;
+    }
+    t_done += steps;
+    s_done += ns;
+  }
+  D2H(hst->z, ds.z, (size_t)C * d * w, s0);
+  D2H(hst->loc, ds.loc, (size_t)C * d * w, s0);
+  D2H(hst->scale, ds.scale, (size_t)C * np * w, s0);
+  D2H(hst->potential_energy, ds.potential_energy, (size_t)C * w, s0);
+  D2H(hst->mean_accept_prob, ds.mean_accept_prob, (size_t)C * w, s0);
+  D2H(hst->log_step_size, ds.log_step_size, (size_t)C * w, s0);
+  D2H(hst->as_change, ds.as_change, (size_t)C * w, s0);
+  if (b_acc) D2H(ha->out_accept, d_acc, (size_t)T * C, s0);
 #undef H2D
 #undef D2H
-  rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize");
-  if (rc) return rc;
+  if ((rc = check_cuda(cudaStreamSynchronize(s0), "cudaStreamSynchronize"))) return rc;
+  if ((rc = check_cuda(cudaStreamSynchronize(s1), "cudaStreamSynchronize"))) return rc;
   hst->i = ds.i;
   return AMCMC_OK;
 }

@@ -20,6 +20,9 @@ struct amcmc_model {
   // scratch for amcmc_arwmh_run_host
   void* scratch;
   size_t scratch_bytes;
+  cudaStream_t host_streams[2];  // [0] compute, [1] device->host sample copies (created lazily)
+  cudaEvent_t host_events[4];    // [0..1] chunk computed, [2..3] chunk copied
+  int host_streams_ready;
 };
 
 namespace amcmc {
@@ -37,5 +40,12 @@ int check_cuda(cudaError_t e, const char* what);
 AMCMC_DECL_FAMILY(std_normal)
 AMCMC_DECL_FAMILY(eight_schools)
 AMCMC_DECL_FAMILY(kidiq)
+
+// diamonds: block-per-chain CUDA-core path (exact) -- block_diamonds.cu
+int create_diamonds(amcmc_model* m, const double* X, int64_t n, int K, const double* Y);
+int run_diamonds_block(const amcmc_model* m, const amcmc_state* st, const amcmc_run_args* a, cudaStream_t s);
+int init_diamonds(const amcmc_model* m, const amcmc_state* st, uint64_t seed, int64_t chain_offset, double radius,
+                  int use_given_z, cudaStream_t s);
+int potential_diamonds_block(const amcmc_model* m, int64_t n, const void* q, void* out, cudaStream_t s);
 
 }  // namespace amcmc

@@ -40,7 +40,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", default="eight_schools", choices=sorted(WORKLOADS))
     p.add_argument("--chains", type=int, default=None, help="chains per GPU")
-    p.add_argument("--mcmc-steps", type=int, default=1000, help="fused ARWMH iterations per bench step")
+    p.add_argument("--mcmc-steps", type=int, default=10000, help="fused ARWMH iterations per bench step")
     p.add_argument("--thinning", type=int, default=50, help="reference thins eight_schools by 50")
     p.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -122,6 +122,9 @@ class ClockSampler:
         self.proc = None
         self.thread = None
 
+    def mark(self):
+        return len(self.rows)
+
     def start(self):
         try:
             self.proc = subprocess.Popen(
@@ -138,7 +141,7 @@ class ClockSampler:
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self):
+    def stop(self, lo=0, hi=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -148,7 +151,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[max(lo - 1, 0):(hi + 1 if hi is not None else None)] or self.rows[-2:]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -197,25 +201,27 @@ def run_ours(args):
     def one_step(collect=True):
         return sampler.run_batch(batch, T, thinning=args.thinning, collect=("z", "potential_energy") if collect else ())
 
-    for _ in range(W):  # warm-up = the sampler's adaptation warm-up phase (W*T iterations)
-        one_step()
-    torch.cuda.synchronize()
-
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(W):  # warm-up = the sampler's adaptation warm-up phase (W*T iterations)
+        one_step()
+    torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     kept = []
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    n_ess = min(Cn, 4096)
+    mark0 = clocks.mark()
     for k in range(K):
         flush.fill_(k & 0xFF)  # L2 flush between timed iterations (not timed)
         ev[k][0].record()
         raw = one_step()
         ev[k][1].record()
-        kept.append(raw["z"])
+        kept.append(raw["z"][:, :, :n_ess].clone())
     torch.cuda.synchronize()
+    mark1 = clocks.mark()
     if world > 1:
         dist.barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -224,15 +230,15 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms_max = float(tmax.item())
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(mark0, mark1) if rank == 0 else None
 
     value = world * Cn * T * K / (ms_max * 1e-3)
 
     # min-ESS/s over the timed (post-warm-up) region: NumPyro-definition ESS over all chains of this rank
     zs = torch.cat(kept, dim=0).permute(2, 0, 1)  # [C, S, d]
-    sub = zs[: min(Cn, 8192)]
-    ess = am.diagnostics.effective_sample_size(sub)
-    min_ess = float(ess.min()) * (Cn / sub.shape[0]) * world
+    ess = am.diagnostics.effective_sample_size(zs)
+    min_ess = float(ess.min()) * (Cn / zs.shape[0]) * world
+    rhat_max = float(am.diagnostics.split_gelman_rubin(zs).max())
     min_ess_per_s = min_ess / (ms_max * 1e-3)
     acc = float(batch.macc.mean())
 
@@ -277,7 +283,9 @@ def run_ours(args):
             "d2h_bytes_per_step": state_bytes + S * (d + 1) * Cn * esz,
             "api": "amcmc_arwmh_run_host (C ABI, pinned host buffers)",
         }
-        launches += K
+        S_ = T // args.thinning
+        chunk_S = min(S_, (2048 + args.thinning - 1) // args.thinning) or 1
+        launches += K * max(1, -(-S_ // chunk_S))
 
     if rank != 0:
         if world > 1:
@@ -320,6 +328,9 @@ def run_ours(args):
         },
         "min_ess_per_sec": min_ess_per_s,
         "mean_accept_prob": acc,
+        "ess_detail": {"chains_used": int(zs.shape[0]), "draws_per_chain": int(zs.shape[1]), "split_rhat_max": rhat_max,
+                       "definition": "numpyro.diagnostics.effective_sample_size (Geyer initial monotone), unconstrained coords, "
+                                     "scaled from chains_used to all chains"},
         "e2e": e2e,
         "gpu_launches": launches,
         "clocks": clk,
