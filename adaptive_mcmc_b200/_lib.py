@@ -62,6 +62,20 @@ class AmcmcRunArgs(C.Structure):
     ]
 
 
+class AmcmcPooled(C.Structure):
+    """struct amcmc_pooled (include/amcmc.h)."""
+
+    _fields_ = [
+        ("dim", C.c_int32),
+        ("dtype", C.c_int32),
+        ("loc", C.c_void_p),
+        ("scale", C.c_void_p),
+        ("log_step_size", C.c_void_p),
+        ("cov", C.c_void_p),
+        ("window", C.c_int64),
+    ]
+
+
 class AmcmcError(RuntimeError):
     pass
 
@@ -78,8 +92,10 @@ EXPORTED_SYMBOLS = (
     "amcmc_arwmh_run",
     "amcmc_potential",
     "amcmc_arwmh_run_host",
+    "amcmc_pooled_run",
     "amcmc_pooled_stats",
-    "amcmc_pooled_set_adapt",
+    "amcmc_pooled_update",
+    "amcmc_selftest_umma",
     "amcmc_last_error",
     "amcmc_version",
 )
@@ -119,12 +135,14 @@ def lib():
     L.amcmc_potential.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.amcmc_arwmh_run_host.restype = C.c_int
     L.amcmc_arwmh_run_host.argtypes = [C.c_void_p, C.POINTER(AmcmcState), C.POINTER(AmcmcRunArgs)]
+    L.amcmc_pooled_run.restype = C.c_int
+    L.amcmc_pooled_run.argtypes = [C.c_void_p, C.POINTER(AmcmcState), C.POINTER(AmcmcPooled), C.POINTER(AmcmcRunArgs), C.c_void_p]
     L.amcmc_pooled_stats.restype = C.c_int
-    L.amcmc_pooled_stats.argtypes = [C.POINTER(AmcmcState), C.c_void_p, C.c_void_p]
-    L.amcmc_pooled_set_adapt.restype = C.c_int
-    L.amcmc_pooled_set_adapt.argtypes = [
-        C.POINTER(AmcmcState), C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p,
-    ]
+    L.amcmc_pooled_stats.argtypes = [C.POINTER(AmcmcState), C.POINTER(AmcmcPooled), C.c_void_p, C.c_void_p]
+    L.amcmc_pooled_update.restype = C.c_int
+    L.amcmc_pooled_update.argtypes = [C.POINTER(AmcmcPooled), C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+    L.amcmc_selftest_umma.restype = C.c_int
+    L.amcmc_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     _lib = L
     return L
 

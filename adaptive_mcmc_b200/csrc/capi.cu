@@ -107,6 +107,7 @@ int amcmc_model_create(amcmc_model** out, int model_id, int dtype, int dim, int 
         break;
       }
       rc = create_diamonds(m, arrays[0], lens[1], dim - 1, arrays[1]);
+      if (!rc) rc = create_diamonds_tc(m, arrays[0], lens[1], dim - 1, arrays[1]);
       break;
     }
     default:
@@ -123,6 +124,7 @@ int amcmc_model_destroy(amcmc_model* m) {
   for (int k = 0; k < 4; ++k)
     if (m->d_arr[k]) cudaFree(m->d_arr[k]);
   if (m->scratch) cudaFree(m->scratch);
+  if (m->model_id == AMCMC_MODEL_DIAMONDS) destroy_diamonds_tc(m);
   if (m->host_streams_ready) {
     for (int k = 0; k < 2; ++k) cudaStreamDestroy(m->host_streams[k]);
     for (int k = 0; k < 4; ++k) cudaEventDestroy(m->host_events[k]);
@@ -337,16 +339,6 @@ int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args*
   if ((rc = check_cuda(cudaStreamSynchronize(s1), "cudaStreamSynchronize"))) return rc;
   hst->i = ds.i;
   return AMCMC_OK;
-}
-
-int amcmc_pooled_stats(const amcmc_state*, double*, void*) {
-  set_error("amcmc_pooled_stats: not available in this build");
-  return AMCMC_ERR_UNSUPPORTED;
-}
-
-int amcmc_pooled_set_adapt(amcmc_state*, const double*, const double*, double, int, void*) {
-  set_error("amcmc_pooled_set_adapt: not available in this build");
-  return AMCMC_ERR_UNSUPPORTED;
 }
 
 }  // extern "C"

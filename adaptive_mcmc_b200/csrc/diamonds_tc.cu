@@ -1,0 +1,500 @@
+// diamonds_tc.cu -- diamonds (N = 5000-row linear regression, d = 26) many-chain Metropolis on the
+// 5th-gen tensor cores: the X*beta likelihood of 128-chain groups is a dense contraction executed by
+// tcgen05.mma (UTCHMMA) with TMA-staged (cp.async.bulk, UBLKCP) design-matrix tiles and fp32
+// accumulators in TMEM; the epilogue reads TMEM (tcgen05.ld) and reduces sum-of-squares per chain.
+//
+// Model: python/scripts/run_diamonds_lr_decay.py:24-40.  Sampler step: python/kernels/arwmh.py:161-178
+// with the adaptation state SHARED by all chains of the launch (the frozen kernel of sample_Pnx,
+// arwmh.py:230-249, and the pooled-adaptation mode of BASELINE.json configs[3]).
+//
+// Numerics.  With a shared reference point q_ref (the pooled mean), Delta = (I', b') - (I_ref, b_ref):
+//     RSS(q') = RSS_ref - 2 Delta.g + sum_n m_n^2,     m = [1 | Xc] Delta,   g = [1|Xc]^T r_ref
+// RSS_ref and g come from the fp64 Gram matrix (tiny, recomputed per window); only sum_n m_n^2 needs
+// the N-row contraction and it is a sum of squares of GEMM outputs (no cancellation).  Operands are
+// split bf16 hi/lo and the three significant cross terms are concatenated along K:
+//     A' = [D_hi | D_lo | D_hi | 0]   (128 chains x 80)      B' = [X_hi | X_hi | X_lo | 0]   (rows x 80)
+// so one K = 80 GEMM (5 UMMA k-steps of 16) yields ~16-bit-mantissa products with fp32 accumulation.
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 = 128 epilogue /
+// sampler threads (thread <-> TMEM lane <-> chain of a 128-chain group).  A CTA owns up to 4 groups per
+// round ("weight stationary": every staged X tile is multiplied against all resident groups, which
+// divides the L2->SMEM tile traffic by the number of groups); TMEM holds two 128x256 fp32 accumulators
+// so the epilogue of one (tile, group) overlaps the MMA of the next.
+#include <cmath>
+#include <vector>
+#include "common.cuh"
+#include "internal.h"
+#include "tc_common.cuh"
+
+namespace amcmc {
+
+using namespace tc;
+
+constexpr int TC_D = 26;          // model dimension
+constexpr int TC_KC = 25;         // [1 | Xc] columns
+constexpr int TC_KP = 80;         // concatenated split-precision K
+constexpr int TC_TILE_N = 256;    // data rows per tile (UMMA N)
+constexpr int TC_M = 128;         // chains per group (UMMA M)
+constexpr int TC_GR = 4;          // groups per round
+constexpr int TC_THREADS = 192;
+constexpr int TC_TILE_BYTES = TC_TILE_N * TC_KP * 2;  // 40960
+constexpr int TC_A_BYTES = TC_M * TC_KP * 2;          // 20480
+constexpr int TC_NP = TC_D * (TC_D + 1) / 2;          // 351
+
+// layout of the per-window reference block (floats)
+constexpr int REF_Q = 0;     // q_ref[26]
+constexpr int REF_G2 = 32;   // 2*g[25]
+constexpr int REF_RSS = 60;  // RSS_ref as a float64 (two float slots, 8-byte aligned)
+constexpr int REF_S = 64;    // S = e^lam L + eps I, packed lower row-major [351]
+constexpr int REF_FLOATS = 64 + 352;
+
+struct DiamondsTcExtra {
+  uint16_t* Xcanon;  // [n_tiles][TC_TILE_BYTES/2] bf16, canonical UMMA tile order
+  int n_tiles;
+  double* gram;      // G[25*25] = X1^T X1, h[25] = X1^T Y, yy   (fp64, device)
+  float* ref;        // [REF_FLOATS] device
+  float* xprop;      // [26][cap] proposal parking buffer
+  int64_t xprop_cap;
+};
+
+struct TcParams {
+  int64_t C;
+  int n_groups;
+  const uint16_t* Xcanon;
+  int n_tiles;
+  const float* ref;
+  float* z;      // [26][C]
+  float* pe;     // [C]
+  float* macc;   // [C] mean accept probability over this launch
+  float* xprop;  // [26][C]
+  int64_t i0, n_steps, thinning, collect_start;
+  uint64_t seed;
+  int64_t chain_offset;
+  const float* normals;   // EXTERNAL [T][26][C]
+  const float* uniforms;  // [T][C]
+  float* out_z;
+  float* out_pe;
+  uint8_t* out_acc;
+  float n_rows;
+  double cst;
+};
+
+__device__ __forceinline__ uint16_t f2bf(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf2f(uint16_t b) { return __bfloat162float(__ushort_as_bfloat16(b)); }
+
+// per-window reference block: q_ref, 2g, RSS_ref (fp64 Gram algebra), S = e^lam L + eps I
+template <typename R>
+__global__ void diamonds_tc_ref_kernel(const double* __restrict__ gram, const R* __restrict__ loc,
+                                       const R* __restrict__ scale_packed, const R* __restrict__ log_step, double eps,
+                                       float* __restrict__ ref) {
+  __shared__ double q[TC_KC];
+  __shared__ double Gq[TC_KC];
+  const int t = threadIdx.x;
+  const double* G = gram;
+  const double* h = gram + TC_KC * TC_KC;
+  const double yy = gram[TC_KC * TC_KC + TC_KC];
+  if (t < TC_KC) q[t] = (double)loc[t];
+  __syncthreads();
+  if (t < TC_KC) {
+    double s = 0;
+    for (int k = 0; k < TC_KC; ++k) s += G[t * TC_KC + k] * q[k];
+    Gq[t] = s;
+    ref[REF_G2 + t] = (float)(2.0 * (h[t] - s));
+  }
+  if (t < TC_D) ref[REF_Q + t] = (float)loc[t];
+  __syncthreads();
+  if (t == 0) {
+    double rss = yy;
+    for (int k = 0; k < TC_KC; ++k) rss += q[k] * (Gq[k] - 2.0 * h[k]);
+    *reinterpret_cast<double*>(ref + REF_RSS) = rss;
+  }
+  const double el = exp((double)log_step[0]);
+  for (int e = t; e < TC_NP; e += blockDim.x) {
+    int i = (int)((sqrtf(1.0f + 8.0f * (float)e) - 1.0f) * 0.5f);
+    while (i * (i + 1) / 2 > e) --i;
+    while ((i + 1) * (i + 2) / 2 <= e) ++i;
+    const int j = e - i * (i + 1) / 2;
+    ref[REF_S + e] = (float)((double)scale_packed[e] * el + (i == j ? eps : 0.0));
+  }
+}
+
+struct TcSmem {
+  static constexpr int OFF_X = 0;                              // 2 stages
+  static constexpr int OFF_A = 2 * TC_TILE_BYTES;              // TC_GR groups
+  static constexpr int OFF_REF = OFF_A + TC_GR * TC_A_BYTES;   // REF_FLOATS floats
+  static constexpr int OFF_BAR = OFF_REF + REF_FLOATS * 4;     // barriers
+  static constexpr int N_BAR = 2 + 2 + 2 + 2 + TC_GR;          // x_full, x_empty, acc_full, acc_empty, a_ready
+  static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
+  static constexpr int BYTES = OFF_TMEM + 16;
+};
+
+// sum of squares of one 128x256 accumulator row (this thread's TMEM lane)
+__device__ __forceinline__ float epilogue_sumsq(uint32_t taddr) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 2
+  for (int c0 = 0; c0 < TC_TILE_N; c0 += 32) {
+    float v[32];
+    tmem_ld_32x32(taddr + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      a0 = fmaf(v[i], v[i], a0);
+      a1 = fmaf(v[i + 1], v[i + 1], a1);
+      a2 = fmaf(v[i + 2], v[i + 2], a2);
+      a3 = fmaf(v[i + 3], v[i + 3], a3);
+    }
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+template <bool EXTERNAL>
+__global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sX = smem + TcSmem::OFF_X;
+  unsigned char* sA = smem + TcSmem::OFF_A;
+  float* sRef = reinterpret_cast<float*>(smem + TcSmem::OFF_REF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::OFF_BAR);
+  uint64_t* x_full = bars;
+  uint64_t* x_empty = bars + 2;
+  uint64_t* acc_full = bars + 4;
+  uint64_t* acc_empty = bars + 6;
+  uint64_t* a_ready = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcSmem::OFF_TMEM);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // groups owned by this CTA: contiguous range, balanced to within one group (host guarantees grid <= n_groups)
+  const int per = p.n_groups / (int)gridDim.x, rem = p.n_groups % (int)gridDim.x;
+  const int g_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int g_count = per + ((int)blockIdx.x < rem ? 1 : 0);
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], TC_M);
+    }
+    for (int g = 0; g < TC_GR; ++g) mbar_init(&a_ready[g], TC_M);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int e = tid; e < REF_FLOATS; e += TC_THREADS) sRef[e] = p.ref[e];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_rounds = (g_count + TC_GR - 1) / TC_GR;
+  uint32_t x_it = 0, acc_it = 0, a_it = 0;  // pipeline iteration counters persist across rounds
+
+  for (int rnd = 0; rnd < n_rounds; ++rnd) {
+    const int G = min(TC_GR, g_count - rnd * TC_GR);
+    const int g0 = g_begin + rnd * TC_GR;
+
+    if (warp == 0) {
+      // ===== TMA producer: stream the X' tiles, one pass per MCMC step =====
+      if (lane == 0) {
+        for (int64_t st = 0; st < p.n_steps; ++st)
+          for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
+            const int s = x_it & 1;
+            mbar_wait(&x_empty[s], ((x_it >> 1) & 1) ^ 1);
+            mbar_arrive_expect_tx(&x_full[s], TC_TILE_BYTES);
+            tma_load_1d(sX + s * TC_TILE_BYTES, p.Xcanon + (size_t)tile * (TC_TILE_BYTES / 2), TC_TILE_BYTES, &x_full[s]);
+          }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer (one thread) =====
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16_f32(TC_M, TC_TILE_N);
+        constexpr uint32_t a_kstride = (TC_M / 8) * 128, b_kstride = (TC_TILE_N / 8) * 128;
+        for (int64_t st = 0; st < p.n_steps; ++st) {
+          for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
+            const int s = x_it & 1;
+            mbar_wait(&x_full[s], (x_it >> 1) & 1);
+            for (int g = 0; g < G; ++g, ++acc_it) {
+              if (tile == 0) mbar_wait(&a_ready[g], (a_it + (uint32_t)st) & 1);
+              const int b = acc_it & 1;
+              mbar_wait(&acc_empty[b], ((acc_it >> 1) & 1) ^ 1);
+              tc_fence_after();
+              const uint32_t a_base = smem_u32(sA + g * TC_A_BYTES), b_base = smem_u32(sX + s * TC_TILE_BYTES);
+#pragma unroll
+              for (int ks = 0; ks < TC_KP / 16; ++ks) {
+                const uint64_t da = make_smem_desc(a_base + 2 * ks * a_kstride, a_kstride, 128);
+                const uint64_t db = make_smem_desc(b_base + 2 * ks * b_kstride, b_kstride, 128);
+                umma_bf16(tmem_base + (uint32_t)(b * TC_TILE_N), da, db, idesc, ks > 0);
+              }
+              umma_commit(&acc_full[b]);
+            }
+            umma_commit(&x_empty[s]);
+          }
+        }
+      }
+    } else {
+      // ===== epilogue / sampler threads: thread <-> chain row of each resident group =====
+      const int q4 = warp & 3;         // TMEM lane quarter this warp may access
+      const int row = q4 * 32 + lane;  // chain row within a group
+      const uint32_t t_lane = (uint32_t)(q4 * 32) << 16;
+      const float* S = sRef + REF_S;
+      float macc_sum[TC_GR];
+#pragma unroll
+      for (int g = 0; g < TC_GR; ++g) macc_sum[g] = 0.f;
+      int64_t until_collect = p.collect_start + p.thinning;
+      int64_t sidx = 0;
+
+      for (int64_t st = 0; st < p.n_steps; ++st) {
+        const int64_t it = p.i0 + st;
+        // The handful of scalar terms of U' is assembled in float64: N*s and the normalisation constant are
+        // O(1e4) and would cost ~1e-3 absolute in fp32 (40 DFMA-class ops per chain-step: negligible).
+        double Up_part[TC_GR];
+        float inv2var[TC_GR], uacc[TC_GR], rss[TC_GR];
+        // ---- proposals (arwmh.py:165-167): x' = x + S z; A' rows; scalar part of U'
+#pragma unroll
+        for (int g = 0; g < TC_GR; ++g) {
+          rss[g] = 0.f;
+          Up_part[g] = 0.0; inv2var[g] = 0.f; uacc[g] = 2.f;
+          if (g < G) {
+            const int64_t c = (int64_t)(g0 + g) * TC_M + row;
+            const bool live = c < p.C;
+            const int64_t cc = live ? c : (p.C - 1);
+            float z[TC_D], u;
+            if (EXTERNAL) {
+#pragma unroll
+              for (int k = 0; k < TC_D; ++k) z[k] = p.normals[(st * TC_D + k) * p.C + cc];
+              u = p.uniforms[st * p.C + cc];
+            } else {
+              const Philox rng(p.seed, (uint64_t)(cc + p.chain_offset));
+              philox_draws<float, TC_D>(rng, (uint64_t)it, z, u);
+            }
+            float xp[TC_D];
+#pragma unroll
+            for (int i = 0; i < TC_D; ++i) {
+              float acc = p.z[(int64_t)i * p.C + cc];
+#pragma unroll
+              for (int j = 0; j <= i; ++j) acc = fmaf(S[i * (i + 1) / 2 + j], z[j], acc);
+              xp[i] = acc;
+              if (live) p.xprop[(int64_t)i * p.C + c] = acc;  // parked until the accept decision
+            }
+            float dq = 0.f;  // Delta . 2g
+            unsigned char* arow = sA + g * TC_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < TC_KC; ++k) {
+              const float dlt = xp[k] - sRef[REF_Q + k];
+              dq = fmaf(dlt, sRef[REF_G2 + k], dq);
+              const uint16_t hi = f2bf(dlt);
+              const uint16_t lo = f2bf(dlt - bf2f(hi));
+              *reinterpret_cast<uint16_t*>(arow + canon_off(row, k, TC_M)) = hi;
+              *reinterpret_cast<uint16_t*>(arow + canon_off(row, TC_KC + k, TC_M)) = lo;
+              *reinterpret_cast<uint16_t*>(arow + canon_off(row, 2 * TC_KC + k, TC_M)) = hi;
+            }
+#pragma unroll
+            for (int k = 3 * TC_KC; k < TC_KP; ++k) *reinterpret_cast<uint16_t*>(arow + canon_off(row, k, TC_M)) = 0;
+            fence_proxy_async_smem();
+            mbar_arrive(&a_ready[g]);
+            float sb = 0.f;
+#pragma unroll
+            for (int k = 1; k < TC_KC; ++k) sb = fmaf(xp[k], xp[k], sb);
+            const float s = xp[TC_D - 1];
+            const float ti = (xp[0] - 8.f) * 0.1f, ts = __expf(s) * 0.1f;
+            inv2var[g] = 0.5f * __expf(-2.f * s);
+            // U' = 1/2 sum b^2 + 2 log1p(ti^2/3) + 2 log1p(ts^2/3) - s + N s + cst + e^{-2s}/2 (RSS_ref - 2 D.g + sum m^2)
+            Up_part[g] = (double)(0.5f * sb + 2.f * log1pf(ti * ti * (1.f / 3.f)) + 2.f * log1pf(ts * ts * (1.f / 3.f))) +
+                         ((double)p.n_rows - 1.0) * (double)s + p.cst +
+                         (double)inv2var[g] * (*reinterpret_cast<const double*>(sRef + REF_RSS) - (double)dq);
+            uacc[g] = u;
+          }
+        }
+        // ---- likelihood: sum_n m_n^2 from the TMEM accumulators
+        for (int tile = 0; tile < p.n_tiles; ++tile) {
+#pragma unroll
+          for (int g = 0; g < TC_GR; ++g) {
+            if (g < G) {
+              const int b = acc_it & 1;
+              mbar_wait(&acc_full[b], (acc_it >> 1) & 1);
+              tc_fence_after();
+              const float ss = epilogue_sumsq(tmem_base + t_lane + (uint32_t)(b * TC_TILE_N));
+              tc_fence_before();
+              mbar_arrive(&acc_empty[b]);
+              rss[g] += ss;
+              ++acc_it;
+            }
+          }
+        }
+        // ---- accept / reject (arwmh.py:170-178)
+        const bool collect_now = (--until_collect == 0);
+        if (collect_now) until_collect = p.thinning;
+#pragma unroll
+        for (int g = 0; g < TC_GR; ++g) {
+          if (g < G) {
+            const int64_t c = (int64_t)(g0 + g) * TC_M + row;
+            if (c < p.C) {
+              float Up = (float)(Up_part[g] + (double)inv2var[g] * (double)rss[g]);
+              if (Up != Up) Up = INFINITY;
+              const float U = p.pe[c];
+              const float e = __expf(U - Up);
+              const float alpha = (e > 1.f) ? 1.f : e;
+              const bool acc = uacc[g] < alpha;
+              macc_sum[g] += alpha;
+              if (acc) {
+#pragma unroll
+                for (int k = 0; k < TC_D; ++k) p.z[(int64_t)k * p.C + c] = p.xprop[(int64_t)k * p.C + c];
+                p.pe[c] = Up;
+              }
+              if (p.out_acc) p.out_acc[st * p.C + c] = (uint8_t)acc;
+              if (collect_now) {
+                if (p.out_z) {
+#pragma unroll
+                  for (int k = 0; k < TC_D; ++k) p.out_z[(sidx * TC_D + k) * p.C + c] = p.z[(int64_t)k * p.C + c];
+                }
+                if (p.out_pe) p.out_pe[sidx * p.C + c] = acc ? Up : U;
+              }
+            }
+          }
+        }
+        if (collect_now) ++sidx;
+      }
+      const float inv_n = 1.f / (float)p.n_steps;
+#pragma unroll
+      for (int g = 0; g < TC_GR; ++g) {
+        if (g < G) {
+          const int64_t c = (int64_t)(g0 + g) * TC_M + row;
+          if (c < p.C) p.macc[c] = macc_sum[g] * inv_n;
+        }
+      }
+    }
+    a_it += (uint32_t)p.n_steps;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static uint16_t host_f2bf(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
+  const uint32_t r = 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)((u + r) >> 16);
+}
+static float host_bf2f(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float x;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+// Build the tensor-core operands of the diamonds design matrix (called from create_diamonds for K = 25).
+int create_diamonds_tc(amcmc_model* m, const double* X, int64_t n, int K, const double* Y) {
+  if (K != TC_KC || m->dtype != AMCMC_F32) return AMCMC_OK;  // tensor path compiled for the posteriordb shape, fp32
+  const int kc = K - 1;
+  std::vector<double> mean(kc, 0.0);
+  for (int k = 0; k < kc; ++k) {
+    for (int64_t r = 0; r < n; ++r) mean[k] += X[r * K + 1 + k];
+    mean[k] /= (double)n;
+  }
+  const int n_tiles = (int)((n + TC_TILE_N - 1) / TC_TILE_N);
+  std::vector<uint16_t> canon((size_t)n_tiles * (TC_TILE_BYTES / 2), 0);
+  std::vector<double> gram(TC_KC * TC_KC + TC_KC + 1, 0.0);
+  std::vector<double> x1(TC_KC);
+  for (int64_t r = 0; r < n; ++r) {
+    x1[0] = 1.0;
+    for (int k = 0; k < kc; ++k) x1[1 + k] = X[r * K + 1 + k] - mean[k];
+    for (int a = 0; a < TC_KC; ++a) {
+      for (int b = 0; b < TC_KC; ++b) gram[a * TC_KC + b] += x1[a] * x1[b];
+      gram[TC_KC * TC_KC + a] += x1[a] * Y[r];
+    }
+    gram[TC_KC * TC_KC + TC_KC] += Y[r] * Y[r];
+    const int tile = (int)(r / TC_TILE_N), rr = (int)(r % TC_TILE_N);
+    uint16_t* t = canon.data() + (size_t)tile * (TC_TILE_BYTES / 2);
+    for (int k = 0; k < TC_KC; ++k) {
+      const float xf = (float)x1[k];
+      const uint16_t hi = host_f2bf(xf);
+      const uint16_t lo = host_f2bf((float)(x1[k] - (double)host_bf2f(hi)));
+      t[canon_off(rr, k, TC_TILE_N) / 2] = hi;               // pairs with D_hi
+      t[canon_off(rr, TC_KC + k, TC_TILE_N) / 2] = hi;       // pairs with D_lo
+      t[canon_off(rr, 2 * TC_KC + k, TC_TILE_N) / 2] = lo;   // pairs with D_hi
+    }
+  }
+  DiamondsTcExtra* ex = (DiamondsTcExtra*)calloc(1, sizeof(DiamondsTcExtra));
+  ex->n_tiles = n_tiles;
+  int rc;
+  if ((rc = check_cuda(cudaMalloc(&ex->Xcanon, canon.size() * 2), "cudaMalloc(Xcanon)"))) return rc;
+  if ((rc = check_cuda(cudaMalloc(&ex->gram, gram.size() * 8), "cudaMalloc(gram)"))) return rc;
+  if ((rc = check_cuda(cudaMalloc(&ex->ref, REF_FLOATS * 4), "cudaMalloc(ref)"))) return rc;
+  if ((rc = check_cuda(cudaMemcpy(ex->Xcanon, canon.data(), canon.size() * 2, cudaMemcpyHostToDevice), "cudaMemcpy"))) return rc;
+  if ((rc = check_cuda(cudaMemcpy(ex->gram, gram.data(), gram.size() * 8, cudaMemcpyHostToDevice), "cudaMemcpy"))) return rc;
+  m->extra = ex;
+  return AMCMC_OK;
+}
+
+void destroy_diamonds_tc(amcmc_model* m) {
+  DiamondsTcExtra* ex = (DiamondsTcExtra*)m->extra;
+  if (!ex) return;
+  if (ex->Xcanon) cudaFree(ex->Xcanon);
+  if (ex->gram) cudaFree(ex->gram);
+  if (ex->ref) cudaFree(ex->ref);
+  if (ex->xprop) cudaFree(ex->xprop);
+  free(ex);
+  m->extra = nullptr;
+}
+
+bool diamonds_tc_available(const amcmc_model* m) { return m->model_id == AMCMC_MODEL_DIAMONDS && m->extra != nullptr; }
+
+// Frozen / pooled run on the tensor cores: all chains share (loc, scale, log_step_size) given as
+// device arrays of the model dtype (fp32).
+int run_diamonds_tc(const amcmc_model* m, const amcmc_state* st, const void* loc, const void* scale_packed,
+                    const void* log_step, const amcmc_run_args* a, cudaStream_t s) {
+  DiamondsTcExtra* ex = (DiamondsTcExtra*)m->extra;
+  if (!ex) { set_error("diamonds tensor-core path needs K = 25 predictors and fp32"); return AMCMC_ERR_UNSUPPORTED; }
+  int rc;
+  if (ex->xprop_cap < st->n_chains) {
+    if (ex->xprop) cudaFree(ex->xprop);
+    ex->xprop = nullptr;
+    ex->xprop_cap = 0;
+    if ((rc = check_cuda(cudaMalloc(&ex->xprop, (size_t)st->n_chains * TC_D * 4), "cudaMalloc(xprop)"))) return rc;
+    ex->xprop_cap = st->n_chains;
+  }
+  diamonds_tc_ref_kernel<float><<<1, 128, 0, s>>>(ex->gram, (const float*)loc, (const float*)scale_packed,
+                                                  (const float*)log_step, a->eps, ex->ref);
+  TcParams p;
+  p.C = st->n_chains;
+  p.n_groups = (int)((st->n_chains + TC_M - 1) / TC_M);
+  p.Xcanon = ex->Xcanon;
+  p.n_tiles = ex->n_tiles;
+  p.ref = ex->ref;
+  p.z = (float*)st->z;
+  p.pe = (float*)st->potential_energy;
+  p.macc = (float*)st->mean_accept_prob;
+  p.xprop = ex->xprop;
+  p.i0 = st->i;
+  p.n_steps = a->n_steps;
+  p.thinning = a->thinning;
+  p.collect_start = a->collect_start;
+  p.seed = a->seed;
+  p.chain_offset = a->chain_offset;
+  p.normals = (const float*)a->normals;
+  p.uniforms = (const float*)a->uniforms;
+  p.out_z = (float*)a->out_z;
+  p.out_pe = (float*)a->out_potential_energy;
+  p.out_acc = a->out_accept;
+  p.n_rows = (float)m->n_rows;
+  p.cst = m->cst;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.n_groups < sms ? p.n_groups : sms;
+  const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
+  if (ext) {
+    if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
+    diamonds_tc_kernel<true><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(p);
+  } else {
+    if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
+    diamonds_tc_kernel<false><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(p);
+  }
+  return check_cuda(cudaGetLastError(), "diamonds_tc_kernel launch");
+}
+
+}  // namespace amcmc

@@ -136,14 +136,46 @@ int amcmc_potential(const amcmc_model* m, int64_t n, const void* q, void* out, v
  * scripts, would bind).  Device scratch is cached inside the model handle. */
 int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* host_state, const amcmc_run_args* host_args);
 
-/* Pooled-adaptation support (BASELINE.json config 4; not in the reference):
- * per-shard sufficient statistics of the current positions, out = [1 + d + d(d+1)/2]
- * float64 on device: (count, sum x_k, sum x_i x_j for j <= i).  The caller
- * all-reduces them (NCCL) and calls amcmc_pooled_set_scale. */
-int amcmc_pooled_stats(const amcmc_state* state, double* out_stats, void* stream);
-/* Broadcast one (loc[d], packed scale[d(d+1)/2], log_step_size) to all chains of the shard. */
-int amcmc_pooled_set_adapt(amcmc_state* state, const double* loc, const double* scale_packed,
-                           double log_step_size, int set_log_step, void* stream);
+/* ---- Pooled adaptation (BASELINE.json configs[3]; NOT in the reference -- spec in DESIGN.md) ----------
+ * All chains of a launch share ONE adaptation state (loc, scale, log_step_size).  Between windows of
+ * K frozen steps the shared state moves by the reference's Robbins-Monro rule (arwmh.py:183-193) with
+ * the chain-average of the innovation:  delta_c = x_c - loc,
+ *     loc += g * mean_c(delta_c);  cov = (1-g) cov + g * mean_c(delta_c delta_c^T);  scale = chol(cov)
+ *     log_step_size += g * (mean accept prob of the window - target);   g = window^-lr_decay
+ * (C = 1, K = 1 reduces to the reference's per-step update).  Sufficient statistics are additive over
+ * shards, so multi-GPU = one all-reduce (NCCL) of 2 + d + d(d+1)/2 doubles per window. */
+typedef struct amcmc_pooled {
+  int32_t dim;
+  int32_t dtype;          /* same dtype as the chain state */
+  void* loc;              /* device [d] */
+  void* scale;            /* device [d(d+1)/2] packed lower triangle, row-major */
+  void* log_step_size;    /* device [1] */
+  double* cov;            /* device [d*d] float64 running covariance */
+  int64_t window;         /* completed adaptation windows (n of the Robbins-Monro schedule) */
+} amcmc_pooled;
+
+/* args->n_steps frozen Metropolis steps for every chain with the shared proposal of *pool
+ * (arwmh.py:161-178 with adapt_state fixed, i.e. the kernel of sample_Pnx :230-249).  Updates state->z,
+ * potential_energy and mean_accept_prob (:= mean acceptance probability of each chain over this call).
+ * diamonds/fp32 runs on the tcgen05 tensor-core path; other models broadcast *pool into the per-chain
+ * adaptation arrays of *state and use the CUDA-core kernels. */
+int amcmc_pooled_run(const amcmc_model* m, amcmc_state* state, const amcmc_pooled* pool, const amcmc_run_args* args,
+                     void* stream);
+/* out_stats (device, float64, ZEROED by this call then accumulated):
+ *   [0] = chains, [1..d] = sum_c delta_k, [1+d .. 1+d+d(d+1)/2) = sum_c delta_i delta_j (j <= i, row-major),
+ *   [1+d+d(d+1)/2] = sum_c mean_accept_prob_c.   Length 2 + d + d(d+1)/2. */
+int amcmc_pooled_stats(const amcmc_state* state, const amcmc_pooled* pool, double* out_stats, void* stream);
+/* Robbins-Monro update of *pool from (all-reduced) statistics; Cholesky on device; pool->window += 1.
+ * A non-positive-definite covariance keeps the previous scale (the reference's NaN guard, arwmh.py:191). */
+int amcmc_pooled_update(amcmc_pooled* pool, const double* stats, double lr_decay, double target_accept_prob,
+                        void* stream);
+
+/* Hardware self-test of the tcgen05 building blocks (UMMA descriptors, TMEM, mbarrier, TMA bulk copy)
+ * used by the diamonds tensor-core path: d_out[128*256] = A[128 x K] * B[256 x K]^T with bf16 inputs
+ * (row-major device arrays of uint16 bf16 bit patterns), fp32 accumulation.  K multiple of 16, <= 96.
+ * scratch: 256*K*2 bytes of device memory (used when use_tma != 0).  No reference counterpart. */
+int amcmc_selftest_umma(const void* a_bf16, const void* b_bf16, int K, void* scratch, float* d_out, int use_tma,
+                        int swap_lbo_sbo, void* stream);
 
 const char* amcmc_last_error(void);
 int amcmc_version(void);

@@ -1,0 +1,157 @@
+"""GPU tests of the tcgen05 tensor-core path (building blocks first, then the diamonds kernel)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import adaptive_mcmc_b200 as am
+from adaptive_mcmc_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("K", [16, 80, 96])
+@pytest.mark.parametrize("use_tma", [0, 1])
+def test_umma_selftest(K, use_tma):
+    g = torch.Generator().manual_seed(K)
+    A = torch.randn(128, K, generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn(256, K, generator=g).to(torch.bfloat16).cuda()
+    D = torch.zeros(128, 256, dtype=torch.float32, device="cuda")
+    scratch = torch.zeros(256 * K, dtype=torch.int16, device="cuda")
+    swap = int(os.environ.get("AMCMC_UMMA_SWAP", "0"))
+    rc = _lib.lib().amcmc_selftest_umma(A.data_ptr(), B.data_ptr(), K, scratch.data_ptr(), D.data_ptr(), use_tma, swap,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "amcmc_selftest_umma")
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    err = (D - ref).abs().max().item()
+    assert err < 1e-3 * (1 + ref.abs().max().item()), f"max err {err}"
+
+
+# ---- diamonds on the tensor cores: frozen / pooled kernel vs the float64 oracle ----------------------
+from adaptive_mcmc_b200 import models
+from adaptive_mcmc_b200.parallel import PooledARWMH
+from oracle import arwmh_numpy as o
+from oracle import pooled_numpy as op
+
+
+@pytest.fixture(scope="module")
+def diamonds_data():
+    return models.synthetic_diamonds(n=5000, k=25, seed=0)
+
+
+def _mode(data):
+    X, Y = data["X"], data["Y"]
+    Xc = np.column_stack([np.ones(len(Y)), X[:, 1:] - X[:, 1:].mean(0)])
+    return np.concatenate([np.linalg.lstsq(Xc, Y, rcond=None)[0], [np.log(0.123)]])
+
+
+@pytest.mark.parametrize("C", [128, 1000])
+def test_diamonds_tc_logdensity_and_trajectory(C, diamonds_data):
+    """Shared draws: the tcgen05 path must take the same accept decisions as the fp64 oracle, and every
+    potential energy it stores must equal the fp64 potential of the stored position (abs 5e-3 on
+    U ~ -3.3e3, i.e. 1.5e-6 relative -- the fp32 reference's own resolution there is 2.4e-4)."""
+    d, T = 26, 12
+    rng = np.random.default_rng(1)
+    q0 = _mode(diamonds_data)[None] + 0.004 * rng.normal(size=(C, d))
+    s = PooledARWMH(models.diamonds, num_chains=C, pool_every=T, init_strategy=am.init_to_value(torch.from_numpy(q0)),
+                    impl=_lib.IMPL_TENSOR)
+    s.init(7, model_kwargs=diamonds_data)
+    # a sensible shared proposal: scale ~ posterior sd
+    s.scale.mul_(0.002)
+    pot = o.make_potential("diamonds", **diamonds_data)
+    z0 = s.batch.z.t().double().cpu().numpy()
+    U0 = pot(z0)
+    np.testing.assert_allclose(s.batch.pe.cpu().numpy(), U0, rtol=2e-5)
+    pool = op.pooled_init(z0)
+    pool["loc"] = s.loc.double().cpu().numpy()
+    pool["L"] = s.dense_scale().double().cpu().numpy()
+    nrm = rng.normal(size=(T, C, d)).astype(np.float32)
+    uni = rng.random(size=(T, C)).astype(np.float32)
+    raw = s.run_window(T, draws=(torch.from_numpy(nrm).permute(0, 2, 1).contiguous(), torch.from_numpy(uni)),
+                       record_accept=True, adapt=True)
+    zo, Uo, pool2, info = op.pooled_window(pot, z0, U0, pool, T, 0, draws=(nrm.astype(np.float64), uni.astype(np.float64)),
+                                           record=True)
+    acc_g = raw["accept"].cpu().numpy().astype(bool)
+    same = (acc_g == info["accepts"]).all(axis=0)
+    assert same.mean() > 0.97, same.mean()
+    assert 0.05 < acc_g.mean() < 0.8
+    zg = raw["z"].permute(0, 2, 1).cpu().numpy().astype(np.float64)  # [T, C, d]
+    peg = raw["potential_energy"].cpu().numpy().astype(np.float64)
+    # (1) stored energy == fp64 potential of the stored position
+    Uchk = pot(zg.reshape(-1, d)).reshape(T, C)
+    assert np.abs(peg - Uchk).max() < 5e-3, np.abs(peg - Uchk).max()
+    # (2) trajectories of the chains with identical decisions
+    assert np.abs(zg[:, same] - info["z"][:, same]).max() < 2e-5
+    # (3) pooled update: mean acceptance, loc, cov -> scale, log_step_size
+    np.testing.assert_allclose(s.batch.macc.cpu().numpy()[same], info["mean_accept"][same], atol=2e-3)
+    if same.all():
+        np.testing.assert_allclose(s.loc.cpu().numpy(), pool2["loc"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(s.cov.cpu().numpy(), pool2["cov"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(s.dense_scale().cpu().numpy(), pool2["L"], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(float(s.log_step_size), pool2["lam"], atol=1e-4)
+    assert s.window == 1
+
+
+def test_diamonds_tc_far_from_reference_point(diamonds_data):
+    """Chains far from q_ref (the transient): Delta is large, the split-bf16 GEMM must still give
+    fp32-class RELATIVE accuracy on the potential."""
+    C, d, T = 256, 26, 4
+    rng = np.random.default_rng(2)
+    q0 = rng.uniform(-2, 2, size=(C, d))
+    s = PooledARWMH(models.diamonds, num_chains=C, pool_every=T, init_strategy=am.init_to_value(torch.from_numpy(q0)),
+                    impl=_lib.IMPL_TENSOR)
+    s.init(3, model_kwargs=diamonds_data)
+    s.scale.mul_(0.05)
+    raw = s.run_window(T, adapt=False)
+    pot = o.make_potential("diamonds", **diamonds_data)
+    zg = raw["z"].permute(0, 2, 1).cpu().numpy().astype(np.float64)
+    peg = raw["potential_energy"].cpu().numpy().astype(np.float64)
+    Uchk = pot(zg.reshape(-1, d)).reshape(T, C)
+    assert (np.abs(peg - Uchk) / np.abs(Uchk)).max() < 2e-5
+
+
+def test_diamonds_tc_matches_cuda_core_frozen_path(diamonds_data):
+    """Same frozen run through the tensor-core kernel and through the exact CUDA-core block kernel
+    (Philox draws): identical accept decisions for almost every chain."""
+    C, d, T = 512, 26, 10
+    rng = np.random.default_rng(4)
+    q0 = _mode(diamonds_data)[None] + 0.004 * rng.normal(size=(C, d))
+    out = {}
+    for impl in (_lib.IMPL_TENSOR, _lib.IMPL_BLOCK):
+        s = PooledARWMH(models.diamonds, num_chains=C, pool_every=T, init_strategy=am.init_to_value(torch.from_numpy(q0)), impl=impl)
+        s.init(5, model_kwargs=diamonds_data)
+        s.scale.mul_(0.002)
+        raw = s.run_window(T, record_accept=True, adapt=False)
+        out[impl] = (raw["accept"].cpu().numpy(), s.batch.z.clone(), s.batch.pe.clone())
+    same = (out[_lib.IMPL_TENSOR][0] == out[_lib.IMPL_BLOCK][0]).all(axis=0)
+    assert same.mean() > 0.97
+    dz = (out[_lib.IMPL_TENSOR][1] - out[_lib.IMPL_BLOCK][1]).abs().cpu().numpy()[:, same]
+    assert dz.max() < 2e-5
+
+
+def test_pooled_adaptation_converges_on_diamonds(diamonds_data):
+    """BASELINE.json configs[3] in miniature: 4096 chains, pooled adaptation every 100 steps; the shared
+    covariance converges to the analytic posterior covariance of the regression coefficients."""
+    C, d = 4096, 26
+    rng = np.random.default_rng(6)
+    q0 = _mode(diamonds_data)[None] + 0.01 * rng.normal(size=(C, d))
+    s = PooledARWMH(models.diamonds, num_chains=C, pool_every=100, init_strategy=am.init_to_value(torch.from_numpy(q0)))
+    s.init(9, model_kwargs=diamonds_data)
+    s.scale.mul_(0.01)
+    s.cov.mul_(1e-4)
+    coll = s.run(6000, thinning=100)
+    X, Y = diamonds_data["X"], diamonds_data["Y"]
+    Xc = X[:, 1:] - X[:, 1:].mean(0)
+    sig = float(torch.exp(coll["z"]["sigma"][-10:]).mean())
+    assert abs(sig - 0.123) < 0.004
+    post_sd = np.sqrt(np.diag(sig**2 * np.linalg.inv(Xc.T @ Xc + sig**2 * np.eye(24))))
+    est_sd = np.sqrt(np.diag(s.cov.cpu().numpy()))[1:25]
+    assert 0.7 < (est_sd / post_sd).min() and (est_sd / post_sd).max() < 1.4, est_sd / post_sd
+    acc = float(s.batch.macc.mean())
+    assert 0.15 < acc < 0.35, acc
+    b_last = coll["z"]["b"][-20:].double().mean((0, 1)).cpu().numpy()
+    ridge = np.linalg.solve(Xc.T @ Xc + sig**2 * np.eye(24), Xc.T @ (Y - Y.mean()))
+    assert (np.abs(b_last - ridge) / post_sd).max() < 0.5
