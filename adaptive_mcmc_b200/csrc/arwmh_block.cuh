@@ -51,7 +51,7 @@ template <typename R> struct DiamondsBlockModel {
   int n_stride;          // leading dimension of XcT
   const R* __restrict__ XcT;  // [kc][n_stride]  (column-major: consecutive threads read consecutive rows)
   const R* __restrict__ Y;    // [n]
-  R cst;
+  double cst;
 
   template <int NT> __device__ R potential(const R* q, R* red) const {
     const R icpt = q[0];
@@ -81,8 +81,12 @@ template <typename R> struct DiamondsBlockModel {
     const R ti = (icpt - (R)8) * (R)0.1;
     const R ts = Num<R>::exp(s) * (R)0.1;
     const R third = (R)(1.0 / 3.0);
-    return (R)0.5 * sb + (R)2 * Num<R>::log1p(ti * ti * third) + (R)2 * Num<R>::log1p(ts * ts * third) - s +
-           (R)n * s + (R)0.5 * Num<R>::exp((R)-2 * s) * rss + cst;
+    // N*s, the normalisation constant and e^{-2s}/2 * RSS are O(1e3..1e4) each and cancel to O(1e3): the
+    // handful of scalar operations is done in float64 even for the fp32 instantiation (an SFU exp or an
+    // fp32 add at 1e4 would each cost ~1e-3 absolute on U)
+    const double inv2var = 0.5 * ::exp(-2.0 * (double)s);
+    return (R)((double)((R)0.5 * sb + (R)2 * Num<R>::log1p(ti * ti * third) + (R)2 * Num<R>::log1p(ts * ts * third)) +
+               ((double)n - 1.0) * (double)s + cst + inv2var * (double)rss);
   }
 };
 

@@ -49,7 +49,7 @@ template <typename R> static DiamondsBlockModel<R> make_dm(const amcmc_model* m)
   b.n_stride = (int)m->arr_len[0];
   b.XcT = (const R*)m->d_arr[0];
   b.Y = (const R*)m->d_arr[1];
-  b.cst = (R)m->cst;
+  b.cst = m->cst;
   return b;
 }
 

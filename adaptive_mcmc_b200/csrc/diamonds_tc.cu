@@ -15,8 +15,10 @@
 //     A' = [D_hi | D_lo | D_hi | 0]   (128 chains x 80)      B' = [X_hi | X_hi | X_lo | 0]   (rows x 80)
 // so one K = 80 GEMM (5 UMMA k-steps of 16) yields ~16-bit-mantissa products with fp32 accumulation.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 = 128 epilogue /
-// sampler threads (thread <-> TMEM lane <-> chain of a 128-chain group).  A CTA owns up to 4 groups per
+// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-9 = 256 epilogue /
+// sampler threads.  Thread (quarter q, lane, half h) <-> TMEM lane (= chain row) 32q+lane; it drains
+// columns [128h, 128h+128) of every accumulator tile (4 tcgen05.ld in flight before one wait) and owns
+// the proposal / accept work of groups {2h, 2h+1} for its chain row.  A CTA owns up to 4 groups per
 // round ("weight stationary": every staged X tile is multiplied against all resident groups, which
 // divides the L2->SMEM tile traffic by the number of groups); TMEM holds two 128x256 fp32 accumulators
 // so the epilogue of one (tile, group) overlaps the MMA of the next.
@@ -36,7 +38,8 @@ constexpr int TC_KP = 80;         // concatenated split-precision K
 constexpr int TC_TILE_N = 256;    // data rows per tile (UMMA N)
 constexpr int TC_M = 128;         // chains per group (UMMA M)
 constexpr int TC_GR = 4;          // groups per round
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;     // 2 per TMEM lane quarter: each drains half the columns of every tile
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // 320
 constexpr int TC_TILE_BYTES = TC_TILE_N * TC_KP * 2;  // 40960
 constexpr int TC_A_BYTES = TC_M * TC_KP * 2;          // 20480
 constexpr int TC_NP = TC_D * (TC_D + 1) / 2;          // 351
@@ -125,26 +128,37 @@ struct TcSmem {
   static constexpr int OFF_BAR = OFF_REF + REF_FLOATS * 4;     // barriers
   static constexpr int N_BAR = 2 + 2 + 2 + 2 + TC_GR;          // x_full, x_empty, acc_full, acc_empty, a_ready
   static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
-  static constexpr int BYTES = OFF_TMEM + 16;
+  static constexpr int OFF_EXCH = OFF_TMEM + 16;               // float [TC_GR][TC_M]: partner's half of sum m^2
+  static constexpr int BYTES = OFF_EXCH + TC_GR * TC_M * 4;
 };
 
-// sum of squares of one 128x256 accumulator row (this thread's TMEM lane)
-__device__ __forceinline__ float epilogue_sumsq(uint32_t taddr) {
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 2
-  for (int c0 = 0; c0 < TC_TILE_N; c0 += 32) {
-    float v[32];
-    tmem_ld_32x32(taddr + (uint32_t)c0, v);
-    tmem_ld_wait();
+// packed fp32x2 FMA on (lo, hi) register pairs: acc += v*v for two accumulator columns at once (FFMA2)
+__device__ __forceinline__ void sq_acc2(float& a_lo, float& a_hi, float v_lo, float v_hi) {
+  asm("{\n\t.reg .b64 rv, ra;\n\t"
+      "mov.b64 rv, {%2, %3};\n\tmov.b64 ra, {%0, %1};\n\t"
+      "fma.rn.f32x2 ra, rv, rv, ra;\n\t"
+      "mov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a_lo), "+f"(a_hi)
+      : "f"(v_lo), "f"(v_hi));
+}
+
+// sum of squares of this thread's TMEM lane over 128 accumulator columns: 4 loads in flight, one wait
+__device__ __forceinline__ float epilogue_sumsq_half(uint32_t taddr) {
+  float v0[32], v1[32], v2[32], v3[32];
+  tmem_ld_32x32(taddr, v0);
+  tmem_ld_32x32(taddr + 32u, v1);
+  tmem_ld_32x32(taddr + 64u, v2);
+  tmem_ld_32x32(taddr + 96u, v3);
+  tmem_ld_wait();
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      a0 = fmaf(v[i], v[i], a0);
-      a1 = fmaf(v[i + 1], v[i + 1], a1);
-      a2 = fmaf(v[i + 2], v[i + 2], a2);
-      a3 = fmaf(v[i + 3], v[i + 3], a3);
-    }
+  for (int i = 0; i < 32; i += 2) {
+    sq_acc2(a0, a1, v0[i], v0[i + 1]);
+    sq_acc2(a2, a3, v1[i], v1[i + 1]);
+    sq_acc2(a4, a5, v2[i], v2[i + 1]);
+    sq_acc2(a6, a7, v3[i], v3[i + 1]);
   }
-  return (a0 + a1) + (a2 + a3);
+  return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
 template <bool EXTERNAL>
@@ -160,6 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
   uint64_t* acc_empty = bars + 6;
   uint64_t* a_ready = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcSmem::OFF_TMEM);
+  float* sExch = reinterpret_cast<float*>(smem + TcSmem::OFF_EXCH);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], TC_M);
+      mbar_init(&acc_empty[s], 32 * TC_EPI_WARPS);
     }
     for (int g = 0; g < TC_GR; ++g) mbar_init(&a_ready[g], TC_M);
     fence_mbar_init();
@@ -232,9 +247,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
       }
     } else {
       // ===== epilogue / sampler threads: thread <-> chain row of each resident group =====
-      const int q4 = warp & 3;         // TMEM lane quarter this warp may access
-      const int row = q4 * 32 + lane;  // chain row within a group
-      const uint32_t t_lane = (uint32_t)(q4 * 32) << 16;
+      const int q4 = warp & 3;             // TMEM lane quarter this warp may access
+      const int half = (warp - 2) >> 2;    // which 128 accumulator columns this thread drains
+      const int row = q4 * 32 + lane;      // chain row within a group
+      const uint32_t t_lane = ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 128);
       const float* S = sRef + REF_S;
       float macc_sum[TC_GR];
 #pragma unroll
@@ -246,14 +262,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
         const int64_t it = p.i0 + st;
         // The handful of scalar terms of U' is assembled in float64: N*s and the normalisation constant are
         // O(1e4) and would cost ~1e-3 absolute in fp32 (40 DFMA-class ops per chain-step: negligible).
-        double Up_part[TC_GR];
-        float inv2var[TC_GR], uacc[TC_GR], rss[TC_GR];
+        double Up_part[TC_GR], inv2var[TC_GR];
+        float uacc[TC_GR], rss[TC_GR];
         // ---- proposals (arwmh.py:165-167): x' = x + S z; A' rows; scalar part of U'
 #pragma unroll
         for (int g = 0; g < TC_GR; ++g) {
           rss[g] = 0.f;
-          Up_part[g] = 0.0; inv2var[g] = 0.f; uacc[g] = 2.f;
-          if (g < G) {
+          Up_part[g] = 0.0; inv2var[g] = 0.0; uacc[g] = 2.f;
+          if (g < G && (g >> 1) == half) {
             const int64_t c = (int64_t)(g0 + g) * TC_M + row;
             const bool live = c < p.C;
             const int64_t cc = live ? c : (p.C - 1);
@@ -296,11 +312,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
             for (int k = 1; k < TC_KC; ++k) sb = fmaf(xp[k], xp[k], sb);
             const float s = xp[TC_D - 1];
             const float ti = (xp[0] - 8.f) * 0.1f, ts = __expf(s) * 0.1f;
-            inv2var[g] = 0.5f * __expf(-2.f * s);
+            // e^{-2s}/2 multiplies RSS ~ 75 into a ~2.5e3 term: an SFU exp (2^-21) would cost ~1e-3 absolute
+            inv2var[g] = 0.5 * exp(-2.0 * (double)s);
             // U' = 1/2 sum b^2 + 2 log1p(ti^2/3) + 2 log1p(ts^2/3) - s + N s + cst + e^{-2s}/2 (RSS_ref - 2 D.g + sum m^2)
             Up_part[g] = (double)(0.5f * sb + 2.f * log1pf(ti * ti * (1.f / 3.f)) + 2.f * log1pf(ts * ts * (1.f / 3.f))) +
                          ((double)p.n_rows - 1.0) * (double)s + p.cst +
-                         (double)inv2var[g] * (*reinterpret_cast<const double*>(sRef + REF_RSS) - (double)dq);
+                         inv2var[g] * (*reinterpret_cast<const double*>(sRef + REF_RSS) - (double)dq);
             uacc[g] = u;
           }
         }
@@ -312,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
               const int b = acc_it & 1;
               mbar_wait(&acc_full[b], (acc_it >> 1) & 1);
               tc_fence_after();
-              const float ss = epilogue_sumsq(tmem_base + t_lane + (uint32_t)(b * TC_TILE_N));
+              const float ss = epilogue_sumsq_half(tmem_base + t_lane + (uint32_t)(b * TC_TILE_N));
               tc_fence_before();
               mbar_arrive(&acc_empty[b]);
               rss[g] += ss;
@@ -320,15 +337,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
             }
           }
         }
+        // ---- exchange the column halves: hand the partial sums of the groups I do not own to my partner
+#pragma unroll
+        for (int g = 0; g < TC_GR; ++g)
+          if (g < G && (g >> 1) != half) sExch[g * TC_M + row] = rss[g];
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+#pragma unroll
+        for (int g = 0; g < TC_GR; ++g)
+          if (g < G && (g >> 1) == half) rss[g] += sExch[g * TC_M + row];
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
         // ---- accept / reject (arwmh.py:170-178)
         const bool collect_now = (--until_collect == 0);
         if (collect_now) until_collect = p.thinning;
 #pragma unroll
         for (int g = 0; g < TC_GR; ++g) {
-          if (g < G) {
+          if (g < G && (g >> 1) == half) {
             const int64_t c = (int64_t)(g0 + g) * TC_M + row;
             if (c < p.C) {
-              float Up = (float)(Up_part[g] + (double)inv2var[g] * (double)rss[g]);
+              float Up = (float)(Up_part[g] + inv2var[g] * (double)rss[g]);
               if (Up != Up) Up = INFINITY;
               const float U = p.pe[c];
               const float e = __expf(U - Up);
@@ -356,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
       const float inv_n = 1.f / (float)p.n_steps;
 #pragma unroll
       for (int g = 0; g < TC_GR; ++g) {
-        if (g < G) {
+        if (g < G && (g >> 1) == half) {
           const int64_t c = (int64_t)(g0 + g) * TC_M + row;
           if (c < p.C) p.macc[c] = macc_sum[g] * inv_n;
         }

@@ -38,7 +38,7 @@ def parse():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--workload", default="eight_schools", choices=sorted(WORKLOADS))
+    p.add_argument("--workload", default="eight_schools", choices=sorted(WORKLOADS) + ["diamonds"])
     p.add_argument("--chains", type=int, default=None, help="chains per GPU")
     p.add_argument("--mcmc-steps", type=int, default=10000, help="fused ARWMH iterations per bench step")
     p.add_argument("--thinning", type=int, default=50, help="reference thins eight_schools by 50")
@@ -185,6 +185,17 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "diamonds":  # secondary workload on its own (profiling, scaling runs)
+        K, W = args.steps, max(args.warmup, 3)
+        res = run_diamonds_tc(args, world, rank, dev, K, W)
+        if rank == 0:
+            res.update({"n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True, "scaling": "weak",
+                        "vs_baseline": None, "dtype": "bf16x3 split (fp32 accumulate)", "data": "synthetic",
+                        "config": {"workload": res.pop("workload")}})
+            print(json.dumps(res))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     wl = WORKLOADS[args.workload]
     Cn = args.chains or wl["chains"]
     T = args.mcmc_steps
@@ -240,6 +251,7 @@ def run_ours(args):
     ess = am.diagnostics.effective_sample_size(zs)
     min_ess = float(ess.min()) * (Cn / zs.shape[0]) * world
     rhat_max = float(am.diagnostics.split_gelman_rubin(zs).max())
+    ess_chains, ess_draws = int(zs.shape[0]), int(zs.shape[1])
     min_ess_per_s = min_ess / (ms_max * 1e-3)
     acc = float(batch.macc.mean())
 
@@ -338,7 +350,7 @@ def run_ours(args):
         },
         "min_ess_per_sec": min_ess_per_s,
         "mean_accept_prob": acc,
-        "ess_detail": {"chains_used": int(zs.shape[0]), "draws_per_chain": int(zs.shape[1]), "split_rhat_max": rhat_max,
+        "ess_detail": {"chains_used": ess_chains, "draws_per_chain": ess_draws, "split_rhat_max": rhat_max,
                        "definition": "numpyro.diagnostics.effective_sample_size (Geyer initial monotone), unconstrained coords, "
                                      "scaled from chains_used to all chains"},
         "e2e": e2e,

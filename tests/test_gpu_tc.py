@@ -51,8 +51,8 @@ def _mode(data):
 @pytest.mark.parametrize("C", [128, 1000])
 def test_diamonds_tc_logdensity_and_trajectory(C, diamonds_data):
     """Shared draws: the tcgen05 path must take the same accept decisions as the fp64 oracle, and every
-    potential energy it stores must equal the fp64 potential of the stored position (abs 5e-3 on
-    U ~ -3.3e3, i.e. 1.5e-6 relative -- the fp32 reference's own resolution there is 2.4e-4)."""
+    potential energy it stores must equal the fp64 potential of the stored position (abs 1e-3 on
+    U ~ -3.3e3, i.e. 3e-7 relative -- the fp32 reference's own resolution there is 2.4e-4)."""
     d, T = 26, 12
     rng = np.random.default_rng(1)
     q0 = _mode(diamonds_data)[None] + 0.004 * rng.normal(size=(C, d))
@@ -82,7 +82,12 @@ def test_diamonds_tc_logdensity_and_trajectory(C, diamonds_data):
     peg = raw["potential_energy"].cpu().numpy().astype(np.float64)
     # (1) stored energy == fp64 potential of the stored position
     Uchk = pot(zg.reshape(-1, d)).reshape(T, C)
-    assert np.abs(peg - Uchk).max() < 5e-3, np.abs(peg - Uchk).max()
+    moved = np.cumsum(acc_g, axis=0) > 0          # energy produced by the tensor-core path
+    err = np.abs(peg - Uchk)
+    assert err[moved].max() < 1e-3, err[moved].max()
+    # energies still equal to U0 come from the fp32 CUDA-core init kernel, whose residual Y - I - Xb cancels
+    # ~6 digits in fp32 exactly as the fp32 reference does (the centred tensor-core path does not)
+    assert err[~moved].max() < 1e-2, err[~moved].max()
     # (2) trajectories of the chains with identical decisions
     assert np.abs(zg[:, same] - info["z"][:, same]).max() < 2e-5
     # (3) pooled update: mean acceptance, loc, cov -> scale, log_step_size
