@@ -15,8 +15,10 @@
 //     A' = [D_hi | D_lo | D_hi | 0]   (128 chains x 80)      B' = [X_hi | X_hi | X_lo | 0]   (rows x 80)
 // so one K = 80 GEMM (5 UMMA k-steps of 16) yields ~16-bit-mantissa products with fp32 accumulation.
 //
-// CTA = 320 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-9 = 256 epilogue /
-// sampler threads.  Thread (quarter q, lane, half h) <-> TMEM lane (= chain row) 32q+lane; it drains
+// CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-9 = 256 epilogue /
+// sampler threads, warps 10-11 = helpers that compute the state-independent half of the NEXT step's
+// proposal (draws, v = S z) while the tensor pipe is busy, so that the step boundary only costs
+// x' = x + v, the bf16 split and ten 16-byte stores per chain.  Thread (quarter q, lane, half h) <-> TMEM lane (= chain row) 32q+lane; it drains
 // columns [128h, 128h+128) of every accumulator tile (4 tcgen05.ld in flight before one wait) and owns
 // the proposal / accept work of groups {2h, 2h+1} for its chain row.  A CTA owns up to 4 groups per
 // round ("weight stationary": every staged X tile is multiplied against all resident groups, which
@@ -39,7 +41,8 @@ constexpr int TC_TILE_N = 256;    // data rows per tile (UMMA N)
 constexpr int TC_M = 128;         // chains per group (UMMA M)
 constexpr int TC_GR = 4;          // groups per round
 constexpr int TC_EPI_WARPS = 8;     // 2 per TMEM lane quarter: each drains half the columns of every tile
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // 320
+constexpr int TC_HELP_WARPS = 2;    // precompute the state-independent half of the next proposal
+constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS + TC_HELP_WARPS);  // 384
 constexpr int TC_TILE_BYTES = TC_TILE_N * TC_KP * 2;  // 40960
 constexpr int TC_A_BYTES = TC_M * TC_KP * 2;          // 20480
 constexpr int TC_NP = TC_D * (TC_D + 1) / 2;          // 351
@@ -48,8 +51,9 @@ constexpr int TC_NP = TC_D * (TC_D + 1) / 2;          // 351
 constexpr int REF_Q = 0;     // q_ref[26]
 constexpr int REF_G2 = 32;   // 2*g[25]
 constexpr int REF_RSS = 60;  // RSS_ref as a float64 (two float slots, 8-byte aligned)
-constexpr int REF_S = 64;    // S = e^lam L + eps I, packed lower row-major [351]
-constexpr int REF_FLOATS = 64 + 352;
+constexpr int REF_S = 64;    // S = e^lam L + eps I, dense lower rows padded to 28 floats (zeros above the diagonal)
+constexpr int REF_SLD = 28;  // row stride of S: 16-byte vector loads, no triangular guards
+constexpr int REF_FLOATS = 64 + TC_D * REF_SLD;
 
 struct DiamondsTcExtra {
   uint16_t* Xcanon;  // [n_tiles][TC_TILE_BYTES/2] bf16, canonical UMMA tile order
@@ -117,8 +121,10 @@ __global__ void diamonds_tc_ref_kernel(const double* __restrict__ gram, const R*
     while (i * (i + 1) / 2 > e) --i;
     while ((i + 1) * (i + 2) / 2 <= e) ++i;
     const int j = e - i * (i + 1) / 2;
-    ref[REF_S + e] = (float)((double)scale_packed[e] * el + (i == j ? eps : 0.0));
+    ref[REF_S + i * REF_SLD + j] = (float)((double)scale_packed[e] * el + (i == j ? eps : 0.0));
   }
+  for (int e = t; e < TC_D * REF_SLD; e += blockDim.x)
+    if (e % REF_SLD > e / REF_SLD) ref[REF_S + e] = 0.f;
 }
 
 struct TcSmem {
@@ -126,10 +132,11 @@ struct TcSmem {
   static constexpr int OFF_A = 2 * TC_TILE_BYTES;              // TC_GR groups
   static constexpr int OFF_REF = OFF_A + TC_GR * TC_A_BYTES;   // REF_FLOATS floats
   static constexpr int OFF_BAR = OFF_REF + REF_FLOATS * 4;     // barriers
-  static constexpr int N_BAR = 2 + 2 + 2 + 2 + TC_GR;          // x_full, x_empty, acc_full, acc_empty, a_ready
+  static constexpr int N_BAR = 2 + 2 + 2 + 2 + 3 * TC_GR;      // x_full, x_empty, acc_full, acc_empty, a_ready, v_full, v_empty
   static constexpr int OFF_TMEM = OFF_BAR + N_BAR * 8;
   static constexpr int OFF_EXCH = OFF_TMEM + 16;               // float [TC_GR][TC_M]: partner's half of sum m^2
-  static constexpr int BYTES = OFF_EXCH + TC_GR * TC_M * 4;
+  static constexpr int OFF_V = OFF_EXCH + TC_GR * TC_M * 4;    // float [TC_GR][27][TC_M]
+  static constexpr int BYTES = OFF_V + TC_GR * 27 * TC_M * 4;
 };
 
 // packed fp32x2 FMA on (lo, hi) register pairs: acc += v*v for two accumulator columns at once (FFMA2)
@@ -173,8 +180,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
   uint64_t* acc_full = bars + 4;
   uint64_t* acc_empty = bars + 6;
   uint64_t* a_ready = bars + 8;
+  uint64_t* v_full = bars + 8 + TC_GR;
+  uint64_t* v_empty = bars + 8 + 2 * TC_GR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcSmem::OFF_TMEM);
   float* sExch = reinterpret_cast<float*>(smem + TcSmem::OFF_EXCH);
+  float* sV = reinterpret_cast<float*>(smem + TcSmem::OFF_V);  // [TC_GR][27][TC_M]: proposal increments + uniform
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -190,7 +200,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 32 * TC_EPI_WARPS);
     }
-    for (int g = 0; g < TC_GR; ++g) mbar_init(&a_ready[g], TC_M);
+    for (int g = 0; g < TC_GR; ++g) {
+      mbar_init(&a_ready[g], TC_M);
+      mbar_init(&v_full[g], 32 * TC_HELP_WARPS);
+      mbar_init(&v_empty[g], TC_M);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -245,66 +259,126 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
           }
         }
       }
-    } else {
-      // ===== epilogue / sampler threads: thread <-> chain row of each resident group =====
-      const int q4 = warp & 3;             // TMEM lane quarter this warp may access
-      const int half = (warp - 2) >> 2;    // which 128 accumulator columns this thread drains
-      const int row = q4 * 32 + lane;      // chain row within a group
-      const uint32_t t_lane = ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 128);
+    } else if (warp >= 2 + TC_EPI_WARPS) {
+      // ===== helper warps: state-independent half of the proposal, one step ahead of the chains =====
+      // v = (e^lam L + eps I) z  and  u   (arwmh.py:162-166,174) for every chain of the resident groups,
+      // computed while the tensor pipe works on the previous step; handed over through shared memory.
+      const int ht = tid - 32 * (2 + TC_EPI_WARPS);  // 0 .. 32*TC_HELP_WARPS-1
       const float* S = sRef + REF_S;
-      float macc_sum[TC_GR];
-#pragma unroll
-      for (int g = 0; g < TC_GR; ++g) macc_sum[g] = 0.f;
-      int64_t until_collect = p.collect_start + p.thinning;
-      int64_t sidx = 0;
-
       for (int64_t st = 0; st < p.n_steps; ++st) {
         const int64_t it = p.i0 + st;
-        // The handful of scalar terms of U' is assembled in float64: N*s and the normalisation constant are
-        // O(1e4) and would cost ~1e-3 absolute in fp32 (40 DFMA-class ops per chain-step: negligible).
-        double Up_part[TC_GR], inv2var[TC_GR];
-        float uacc[TC_GR], rss[TC_GR];
-        // ---- proposals (arwmh.py:165-167): x' = x + S z; A' rows; scalar part of U'
-#pragma unroll
-        for (int g = 0; g < TC_GR; ++g) {
-          rss[g] = 0.f;
-          Up_part[g] = 0.0; inv2var[g] = 0.0; uacc[g] = 2.f;
-          if (g < G && (g >> 1) == half) {
+        for (int g = 0; g < G; ++g) {
+          mbar_wait(&v_empty[g], ((a_it + (uint32_t)st) & 1) ^ 1);
+          for (int row = ht; row < TC_M; row += 32 * TC_HELP_WARPS) {
             const int64_t c = (int64_t)(g0 + g) * TC_M + row;
-            const bool live = c < p.C;
-            const int64_t cc = live ? c : (p.C - 1);
-            float z[TC_D], u;
+            const int64_t cc = c < p.C ? c : (p.C - 1);
+            float z[REF_SLD], u;
             if (EXTERNAL) {
 #pragma unroll
               for (int k = 0; k < TC_D; ++k) z[k] = p.normals[(st * TC_D + k) * p.C + cc];
               u = p.uniforms[st * p.C + cc];
             } else {
+              float zz[TC_D];
               const Philox rng(p.seed, (uint64_t)(cc + p.chain_offset));
-              philox_draws<float, TC_D>(rng, (uint64_t)it, z, u);
+              philox_draws<float, TC_D>(rng, (uint64_t)it, zz, u);
+#pragma unroll
+              for (int k = 0; k < TC_D; ++k) z[k] = zz[k];
             }
-            float xp[TC_D];
+#pragma unroll
+            for (int k = TC_D; k < REF_SLD; ++k) z[k] = 0.f;
+            float* vrow = sV + (size_t)g * 27 * TC_M + row;
 #pragma unroll
             for (int i = 0; i < TC_D; ++i) {
-              float acc = p.z[(int64_t)i * p.C + cc];
+              float acc = 0.f;
 #pragma unroll
-              for (int j = 0; j <= i; ++j) acc = fmaf(S[i * (i + 1) / 2 + j], z[j], acc);
-              xp[i] = acc;
-              if (live) p.xprop[(int64_t)i * p.C + c] = acc;  // parked until the accept decision
+              for (int j4 = 0; j4 <= i / 4; ++j4) {  // 16-byte broadcast loads of the shared proposal factor
+                const float4 s4 = *reinterpret_cast<const float4*>(S + i * REF_SLD + 4 * j4);
+                acc = fmaf(s4.x, z[4 * j4], acc);
+                acc = fmaf(s4.y, z[4 * j4 + 1], acc);
+                acc = fmaf(s4.z, z[4 * j4 + 2], acc);
+                acc = fmaf(s4.w, z[4 * j4 + 3], acc);
+              }
+              vrow[i * TC_M] = acc;
             }
+            vrow[26 * TC_M] = u;
+          }
+          mbar_arrive(&v_full[g]);
+        }
+      }
+    } else {
+      // ===== epilogue / sampler threads =====
+      const int q4 = warp & 3;             // TMEM lane quarter this warp may access
+      const int half = (warp - 2) >> 2;    // which 128 accumulator columns this thread drains
+      const int row = q4 * 32 + lane;      // chain row within a group
+      const uint32_t t_lane = ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 128);
+      // per owned group (g = 2*half + o): energy, position-buffer selector, acceptance sum live in registers
+      float Ucur[2], macc_sum[2];
+      int cur[2];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const int g = 2 * half + o;
+        const int64_t c = (int64_t)(g0 + g) * TC_M + row;
+        Ucur[o] = (g < G && c < p.C) ? p.pe[c] : 0.f;
+        macc_sum[o] = 0.f;
+        cur[o] = 0;
+      }
+      int64_t until_collect = p.collect_start + p.thinning;
+      int64_t sidx = 0;
+
+      for (int64_t st = 0; st < p.n_steps; ++st) {
+        // The handful of scalar terms of U' is assembled in float64: N*s and the normalisation constant are
+        // O(1e4) and would cost ~1e-3 absolute in fp32 (40 DFMA-class ops per chain-step: negligible).
+        double Up_part[2], inv2var[2];
+        float uacc[2], rss[TC_GR];
+#pragma unroll
+        for (int g = 0; g < TC_GR; ++g) rss[g] = 0.f;
+        // ---- proposals (arwmh.py:167): x' = x + v; A' rows; scalar part of U'
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int g = 2 * half + o;
+          Up_part[o] = 0.0; inv2var[o] = 0.0; uacc[o] = 2.f;
+          if (g < G) {
+            const int64_t c = (int64_t)(g0 + g) * TC_M + row;
+            const bool live = c < p.C;
+            const int64_t cc = live ? c : (p.C - 1);
+            const float* xsrc = cur[o] ? p.xprop : p.z;
+            float* xdst = cur[o] ? p.z : p.xprop;
+            float xp[TC_D];
+#pragma unroll
+            for (int i = 0; i < TC_D; ++i) xp[i] = xsrc[(int64_t)i * p.C + cc];
+            mbar_wait(&v_full[g], (a_it + (uint32_t)st) & 1);
+            const float* vrow = sV + (size_t)g * 27 * TC_M + row;
+#pragma unroll
+            for (int i = 0; i < TC_D; ++i) {
+              xp[i] += vrow[i * TC_M];
+              if (live) xdst[(int64_t)i * p.C + c] = xp[i];  // the proposal lives in the other position buffer
+            }
+            uacc[o] = vrow[26 * TC_M];
+            mbar_arrive(&v_empty[g]);
             float dq = 0.f;  // Delta . 2g
-            unsigned char* arow = sA + g * TC_A_BYTES;
+            uint16_t ak[TC_KP];  // this chain's row of A' = [D_hi | D_lo | D_hi | 0]
 #pragma unroll
             for (int k = 0; k < TC_KC; ++k) {
               const float dlt = xp[k] - sRef[REF_Q + k];
               dq = fmaf(dlt, sRef[REF_G2 + k], dq);
               const uint16_t hi = f2bf(dlt);
-              const uint16_t lo = f2bf(dlt - bf2f(hi));
-              *reinterpret_cast<uint16_t*>(arow + canon_off(row, k, TC_M)) = hi;
-              *reinterpret_cast<uint16_t*>(arow + canon_off(row, TC_KC + k, TC_M)) = lo;
-              *reinterpret_cast<uint16_t*>(arow + canon_off(row, 2 * TC_KC + k, TC_M)) = hi;
+              ak[k] = hi;
+              ak[TC_KC + k] = f2bf(dlt - bf2f(hi));
+              ak[2 * TC_KC + k] = hi;
             }
 #pragma unroll
-            for (int k = 3 * TC_KC; k < TC_KP; ++k) *reinterpret_cast<uint16_t*>(arow + canon_off(row, k, TC_M)) = 0;
+            for (int k = 3 * TC_KC; k < TC_KP; ++k) ak[k] = 0;
+            // one 16-byte store per 8-element K chunk (= one core-matrix row of the canonical layout)
+            unsigned char* arow = sA + g * TC_A_BYTES + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+            for (int kc = 0; kc < TC_KP / 8; ++kc) {
+              uint4 v;
+              v.x = (uint32_t)ak[8 * kc] | ((uint32_t)ak[8 * kc + 1] << 16);
+              v.y = (uint32_t)ak[8 * kc + 2] | ((uint32_t)ak[8 * kc + 3] << 16);
+              v.z = (uint32_t)ak[8 * kc + 4] | ((uint32_t)ak[8 * kc + 5] << 16);
+              v.w = (uint32_t)ak[8 * kc + 6] | ((uint32_t)ak[8 * kc + 7] << 16);
+              *reinterpret_cast<uint4*>(arow + kc * (TC_M / 8) * 128) = v;
+            }
             fence_proxy_async_smem();
             mbar_arrive(&a_ready[g]);
             float sb = 0.f;
@@ -313,15 +387,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
             const float s = xp[TC_D - 1];
             const float ti = (xp[0] - 8.f) * 0.1f, ts = __expf(s) * 0.1f;
             // e^{-2s}/2 multiplies RSS ~ 75 into a ~2.5e3 term: an SFU exp (2^-21) would cost ~1e-3 absolute
-            inv2var[g] = 0.5 * exp(-2.0 * (double)s);
-            // U' = 1/2 sum b^2 + 2 log1p(ti^2/3) + 2 log1p(ts^2/3) - s + N s + cst + e^{-2s}/2 (RSS_ref - 2 D.g + sum m^2)
-            Up_part[g] = (double)(0.5f * sb + 2.f * log1pf(ti * ti * (1.f / 3.f)) + 2.f * log1pf(ts * ts * (1.f / 3.f))) +
+            inv2var[o] = 0.5 * exp(-2.0 * (double)s);
+            // U' = 1/2 sum b^2 + 2 log1p(ti^2/3) + 2 log1p(ts^2/3) + (N-1) s + cst + e^{-2s}/2 (RSS_ref - 2 D.g + sum m^2)
+            Up_part[o] = (double)(0.5f * sb + 2.f * log1pf(ti * ti * (1.f / 3.f)) + 2.f * log1pf(ts * ts * (1.f / 3.f))) +
                          ((double)p.n_rows - 1.0) * (double)s + p.cst +
-                         inv2var[g] * (*reinterpret_cast<const double*>(sRef + REF_RSS) - (double)dq);
-            uacc[g] = u;
+                         inv2var[o] * (*reinterpret_cast<const double*>(sRef + REF_RSS) - (double)dq);
           }
         }
-        // ---- likelihood: sum_n m_n^2 from the TMEM accumulators
+        // ---- likelihood: sum_n m_n^2 from the TMEM accumulators (this thread's 128 columns of every tile)
         for (int tile = 0; tile < p.n_tiles; ++tile) {
 #pragma unroll
           for (int g = 0; g < TC_GR; ++g) {
@@ -342,49 +415,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
         for (int g = 0; g < TC_GR; ++g)
           if (g < G && (g >> 1) != half) sExch[g * TC_M + row] = rss[g];
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        float mine[2];
 #pragma unroll
-        for (int g = 0; g < TC_GR; ++g)
-          if (g < G && (g >> 1) == half) rss[g] += sExch[g * TC_M + row];
+        for (int o = 0; o < 2; ++o) {
+          const int g = 2 * half + o;
+          mine[o] = (g < G) ? rss[g] + sExch[g * TC_M + row] : 0.f;
+        }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-        // ---- accept / reject (arwmh.py:170-178)
+        // ---- accept / reject (arwmh.py:170-178): flip the position-buffer selector instead of copying
         const bool collect_now = (--until_collect == 0);
         if (collect_now) until_collect = p.thinning;
 #pragma unroll
-        for (int g = 0; g < TC_GR; ++g) {
-          if (g < G && (g >> 1) == half) {
+        for (int o = 0; o < 2; ++o) {
+          const int g = 2 * half + o;
+          if (g < G) {
             const int64_t c = (int64_t)(g0 + g) * TC_M + row;
             if (c < p.C) {
-              float Up = (float)(Up_part[g] + inv2var[g] * (double)rss[g]);
+              float Up = (float)(Up_part[o] + inv2var[o] * (double)mine[o]);
               if (Up != Up) Up = INFINITY;
-              const float U = p.pe[c];
-              const float e = __expf(U - Up);
+              const float e = __expf(Ucur[o] - Up);
               const float alpha = (e > 1.f) ? 1.f : e;
-              const bool acc = uacc[g] < alpha;
-              macc_sum[g] += alpha;
-              if (acc) {
-#pragma unroll
-                for (int k = 0; k < TC_D; ++k) p.z[(int64_t)k * p.C + c] = p.xprop[(int64_t)k * p.C + c];
-                p.pe[c] = Up;
-              }
+              const bool acc = uacc[o] < alpha;
+              macc_sum[o] += alpha;
+              if (acc) { cur[o] ^= 1; Ucur[o] = Up; }
               if (p.out_acc) p.out_acc[st * p.C + c] = (uint8_t)acc;
               if (collect_now) {
                 if (p.out_z) {
+                  const float* xs = cur[o] ? p.xprop : p.z;
 #pragma unroll
-                  for (int k = 0; k < TC_D; ++k) p.out_z[(sidx * TC_D + k) * p.C + c] = p.z[(int64_t)k * p.C + c];
+                  for (int k = 0; k < TC_D; ++k) p.out_z[(sidx * TC_D + k) * p.C + c] = xs[(int64_t)k * p.C + c];
                 }
-                if (p.out_pe) p.out_pe[sidx * p.C + c] = acc ? Up : U;
+                if (p.out_pe) p.out_pe[sidx * p.C + c] = Ucur[o];
               }
             }
           }
         }
         if (collect_now) ++sidx;
       }
+      // ---- write back: energy, mean acceptance, and the position if it ended in the shadow buffer
       const float inv_n = 1.f / (float)p.n_steps;
 #pragma unroll
-      for (int g = 0; g < TC_GR; ++g) {
-        if (g < G && (g >> 1) == half) {
+      for (int o = 0; o < 2; ++o) {
+        const int g = 2 * half + o;
+        if (g < G) {
           const int64_t c = (int64_t)(g0 + g) * TC_M + row;
-          if (c < p.C) p.macc[c] = macc_sum[g] * inv_n;
+          if (c < p.C) {
+            p.pe[c] = Ucur[o];
+            p.macc[c] = macc_sum[o] * inv_n;
+            if (cur[o]) {
+#pragma unroll
+              for (int k = 0; k < TC_D; ++k) p.z[(int64_t)k * p.C + c] = p.xprop[(int64_t)k * p.C + c];
+            }
+          }
         }
       }
     }
