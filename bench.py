@@ -325,7 +325,7 @@ def run_ours(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(f"{args.workload}_{args.dtype}")
+        traffic = json.load(open(tp)).get(f"{args.workload}_{args.dtype}_T{T}")  # ncu capture of this exact launch shape
     line = {
         "metric": "chain-steps/sec",
         "value": value,
@@ -475,11 +475,16 @@ def run_diamonds_tc(args, world, rank, dev, K, W):
             "bound": "tensor", "unit": "TFLOP/s", "peak": peak,
             "achieved": per_gpu * 240000 * 3 / 1e12, "frac": per_gpu * 240000 * 3 / 1e12 / peak,
             "executed_tflops": per_gpu * 2 * 5120 * 80 / 1e12, "executed_frac": per_gpu * 2 * 5120 * 80 / 1e12 / peak,
-            "algorithmic_single_pass_tflops": per_gpu * 240000 / 1e12, "traffic": None,
+            "algorithmic_single_pass_tflops": per_gpu * 240000 / 1e12, "traffic": _traffic("diamonds_tc_window100"),
             "note": "achieved = chain-steps/s x 2*N*Kc (240,000 flop, SURVEY 8d) x 3 split-bf16 passes; executed = incl. K padding 75->80 "
                     "and row padding 5000->5120; peak = MEASURED_PEAKS.json bf16_tflops_sustained (of measured)",
         },
     }
+
+
+def _traffic(key):
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(tp)).get(key) if os.path.exists(tp) else None
 
 
 def main():
