@@ -92,6 +92,7 @@ EXPORTED_SYMBOLS = (
     "amcmc_arwmh_run",
     "amcmc_potential",
     "amcmc_arwmh_run_host",
+    "amcmc_arwmh_init_host",
     "amcmc_pooled_run",
     "amcmc_pooled_stats",
     "amcmc_pooled_update",
@@ -135,6 +136,8 @@ def lib():
     L.amcmc_potential.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.amcmc_arwmh_run_host.restype = C.c_int
     L.amcmc_arwmh_run_host.argtypes = [C.c_void_p, C.POINTER(AmcmcState), C.POINTER(AmcmcRunArgs)]
+    L.amcmc_arwmh_init_host.restype = C.c_int
+    L.amcmc_arwmh_init_host.argtypes = [C.c_void_p, C.POINTER(AmcmcState), C.c_uint64, C.c_int64, C.c_double, C.c_int]
     L.amcmc_pooled_run.restype = C.c_int
     L.amcmc_pooled_run.argtypes = [C.c_void_p, C.POINTER(AmcmcState), C.POINTER(AmcmcPooled), C.POINTER(AmcmcRunArgs), C.c_void_p]
     L.amcmc_pooled_stats.restype = C.c_int

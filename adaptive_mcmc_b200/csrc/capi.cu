@@ -222,6 +222,43 @@ int amcmc_potential(const amcmc_model* m, int64_t n, const void* q, void* out, v
   return AMCMC_ERR_UNSUPPORTED;
 }
 
+// ARWMH.init with host buffers: device scratch, init kernel, copy everything back.
+int amcmc_arwmh_init_host(amcmc_model* m, amcmc_state* hst, uint64_t seed, int64_t chain_offset, double init_radius,
+                          int use_given_z) {
+  int rc = validate_state(m, hst, "amcmc_arwmh_init_host");
+  if (rc) return rc;
+  const size_t w = elt(m->dtype);
+  const int64_t C = hst->n_chains, d = hst->dim, np = d * (d + 1) / 2;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_vec = al((size_t)C * w), b_mat = al((size_t)C * d * w), b_tri = al((size_t)C * np * w);
+  const size_t total = 4 * b_vec + 2 * b_mat + b_tri;
+  if (m->scratch_bytes < total) {
+    if (m->scratch) cudaFree(m->scratch);
+    m->scratch = nullptr;
+    m->scratch_bytes = 0;
+    if ((rc = check_cuda(cudaMalloc(&m->scratch, total), "cudaMalloc(init_host scratch)"))) return rc;
+    m->scratch_bytes = total;
+  }
+  char* p = (char*)m->scratch;
+  auto take = [&](size_t b) { char* q = p; p += b; return (void*)q; };
+  amcmc_state ds = *hst;
+  ds.z = take(b_mat); ds.loc = take(b_mat); ds.scale = take(b_tri);
+  ds.potential_energy = take(b_vec); ds.mean_accept_prob = take(b_vec);
+  ds.log_step_size = take(b_vec); ds.as_change = take(b_vec);
+  cudaStream_t s = 0;
+  if (use_given_z && (rc = check_cuda(cudaMemcpyAsync(ds.z, hst->z, (size_t)C * d * w, cudaMemcpyHostToDevice, s), "H2D"))) return rc;
+  if ((rc = amcmc_arwmh_init(m, &ds, seed, chain_offset, init_radius, use_given_z, (void*)s))) return rc;
+  struct { void* h; void* d; size_t n; } cp[] = {
+      {hst->z, ds.z, (size_t)C * d * w}, {hst->loc, ds.loc, (size_t)C * d * w}, {hst->scale, ds.scale, (size_t)C * np * w},
+      {hst->potential_energy, ds.potential_energy, (size_t)C * w}, {hst->mean_accept_prob, ds.mean_accept_prob, (size_t)C * w},
+      {hst->log_step_size, ds.log_step_size, (size_t)C * w}, {hst->as_change, ds.as_change, (size_t)C * w}};
+  for (auto& c : cp)
+    if ((rc = check_cuda(cudaMemcpyAsync(c.h, c.d, c.n, cudaMemcpyDeviceToHost, s), "D2H"))) return rc;
+  if ((rc = check_cuda(cudaStreamSynchronize(s), "cudaStreamSynchronize"))) return rc;
+  hst->i = 0;
+  return AMCMC_OK;
+}
+
 // Host-buffer variant: H2D state (+ draws), fused run, D2H state + samples.  Pointers in
 // *hst / *ha are host memory (pinned memory makes the copies truly asynchronous).  The run is cut
 // into chunks of whole thinning periods; chunk k's samples travel device->host on a second stream

@@ -135,6 +135,9 @@ int amcmc_potential(const amcmc_model* m, int64_t n, const void* q, void* out, v
  * returning (this is what a non-CUDA caller, e.g. the reference's NumPy/JAX-CPU
  * scripts, would bind).  Device scratch is cached inside the model handle. */
 int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* host_state, const amcmc_run_args* host_args);
+/* amcmc_arwmh_init with HOST buffers in *host_state (same contract; synchronises before returning). */
+int amcmc_arwmh_init_host(amcmc_model* m, amcmc_state* host_state, uint64_t seed, int64_t chain_offset,
+                          double init_radius, int use_given_z);
 
 /* ---- Pooled adaptation (BASELINE.json configs[3]; NOT in the reference -- spec in DESIGN.md) ----------
  * All chains of a launch share ONE adaptation state (loc, scale, log_step_size).  Between windows of

@@ -240,3 +240,22 @@ def test_run_host_entry_point_matches_device_path():
     assert hs.i == T
     torch.testing.assert_close(oz, raw["z"].cpu(), rtol=0, atol=0)
     torch.testing.assert_close(host["scale"], b.scale.cpu(), rtol=0, atol=0)
+
+
+def test_reference_binding_example():
+    """the torch-free ctypes stub over the host-buffer entry points."""
+    import importlib.util, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "reference_binding.py")
+    spec = importlib.util.spec_from_file_location("reference_binding", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    k = mod.B200ARWMH("eight_schools", num_chains=512, y=models.eight_schools.Y, sigma=models.eight_schools.SIGMA)
+    st = k.init(3)
+    np.testing.assert_array_equal(st["z"].T, co.init_uniform(3, 512, 10, dt=np.float32))
+    np.testing.assert_allclose(st["potential_energy"], o.potential_eight_schools(st["z"].T.astype(np.float64)), rtol=1e-5)
+    z, st = k.run(st, 20000, num_warmup=5000, thinning=50)
+    assert z.shape == (300, 512, 10) and st["i"] == 20000
+    assert 0.15 < float(st["mean_accept_prob"].mean()) < 0.3
+    assert abs(float(z[..., 0].mean()) - 4.4) < 0.5
+    with pytest.raises(ValueError):
+        mod.B200ARWMH("eight_schools", num_chains=4, y=[1.0], sigma=[1.0])
