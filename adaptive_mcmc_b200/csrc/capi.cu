@@ -110,6 +110,15 @@ int amcmc_model_create(amcmc_model** out, int model_id, int dtype, int dim, int 
       if (!rc) rc = create_diamonds_tc(m, arrays[0], lens[1], dim - 1, arrays[1]);
       break;
     }
+    case AMCMC_MODEL_GAUSSIAN: {
+      if (n_arrays != 1 || dim < 1 || lens[0] != (int64_t)dim * dim) {
+        set_error("gaussian: expects P[d*d] (row-major lower Cholesky factor of the precision)");
+        rc = AMCMC_ERR_ARG;
+        break;
+      }
+      rc = create_gaussian(m, arrays[0], dim);
+      break;
+    }
     default:
       set_error("model id %d not available in this build", model_id);
       rc = AMCMC_ERR_UNSUPPORTED;
@@ -161,6 +170,7 @@ int amcmc_arwmh_init(const amcmc_model* m, amcmc_state* st, uint64_t seed, int64
     case AMCMC_MODEL_EIGHT_SCHOOLS: return init_eight_schools(m, st, seed, chain_offset, init_radius, use_given_z, s);
     case AMCMC_MODEL_KIDIQ: return init_kidiq(m, st, seed, chain_offset, init_radius, use_given_z, s);
     case AMCMC_MODEL_DIAMONDS: return init_diamonds(m, st, seed, chain_offset, init_radius, use_given_z, s);
+    case AMCMC_MODEL_GAUSSIAN: return init_gaussian(m, st, seed, chain_offset, init_radius, use_given_z, s);
   }
   set_error("amcmc_arwmh_init: unsupported model %d", m->model_id);
   return AMCMC_ERR_UNSUPPORTED;
@@ -191,7 +201,7 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
   if (rc) return rc;
   if (a->n_steps == 0) return AMCMC_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (a->kernel_kind != AMCMC_KERNEL_ARWMH) {
+  if (a->kernel_kind != AMCMC_KERNEL_ARWMH && !(a->kernel_kind == AMCMC_KERNEL_RAM && m->model_id == AMCMC_MODEL_GAUSSIAN)) {
     set_error("amcmc_arwmh_run: kernel kind %d not available for model %d", a->kernel_kind, m->model_id);
     return AMCMC_ERR_UNSUPPORTED;
   }
@@ -200,6 +210,7 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
     case AMCMC_MODEL_EIGHT_SCHOOLS: rc = run_eight_schools(m, st, a, s); break;
     case AMCMC_MODEL_KIDIQ: rc = run_kidiq(m, st, a, s); break;
     case AMCMC_MODEL_DIAMONDS: rc = run_diamonds_block(m, st, a, s); break;
+    case AMCMC_MODEL_GAUSSIAN: rc = run_gaussian(m, st, a, s); break;
     default:
       set_error("amcmc_arwmh_run: unsupported model %d", m->model_id);
       rc = AMCMC_ERR_UNSUPPORTED;
@@ -217,6 +228,7 @@ int amcmc_potential(const amcmc_model* m, int64_t n, const void* q, void* out, v
     case AMCMC_MODEL_EIGHT_SCHOOLS: return potential_eight_schools(m, n, q, out, s);
     case AMCMC_MODEL_KIDIQ: return potential_kidiq(m, n, q, out, s);
     case AMCMC_MODEL_DIAMONDS: return potential_diamonds_block(m, n, q, out, s);
+    case AMCMC_MODEL_GAUSSIAN: return potential_gaussian(m, n, q, out, s);
   }
   set_error("amcmc_potential: unsupported model %d", m->model_id);
   return AMCMC_ERR_UNSUPPORTED;

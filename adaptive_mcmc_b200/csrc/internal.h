@@ -47,6 +47,12 @@ int run_diamonds_block(const amcmc_model* m, const amcmc_state* st, const amcmc_
 int init_diamonds(const amcmc_model* m, const amcmc_state* st, uint64_t seed, int64_t chain_offset, double radius,
                   int use_given_z, cudaStream_t s);
 int potential_diamonds_block(const amcmc_model* m, int64_t n, const void* q, void* out, cudaStream_t s);
+// gaussian: block-per-chain ARWMH (d <= 32) and RAM (d <= 256) -- block_gaussian.cu
+int create_gaussian(amcmc_model* m, const double* P, int d);
+int run_gaussian(const amcmc_model* m, const amcmc_state* st, const amcmc_run_args* a, cudaStream_t s);
+int init_gaussian(const amcmc_model* m, const amcmc_state* st, uint64_t seed, int64_t chain_offset, double radius,
+                  int use_given_z, cudaStream_t s);
+int potential_gaussian(const amcmc_model* m, int64_t n, const void* q, void* out, cudaStream_t s);
 // diamonds: tcgen05 tensor-core path (shared adaptation state) -- diamonds_tc.cu
 int create_diamonds_tc(amcmc_model* m, const double* X, int64_t n, int K, const double* Y);
 void destroy_diamonds_tc(amcmc_model* m);

@@ -71,13 +71,13 @@ class PotentialFn:
         return self._handle
 
     def __del__(self):
-        h = getattr(self, "_handle", None)
-        if h is not None and h.value:
-            try:
+        try:  # may run during interpreter shutdown, when module globals are already gone
+            h = getattr(self, "_handle", None)
+            if h is not None and h.value:
                 _lib.lib().amcmc_model_destroy(h)
-            except Exception:
-                pass
-            self._handle = C.c_void_p()
+                self._handle = None
+        except Exception:
+            pass
 
     # ---- flat <-> dict ----------------------------------------------------
     def ravel(self, z):
@@ -267,7 +267,14 @@ def synthetic_kidiq(n=434, seed=0):
 
 def ar1_precision_chol(d=200, rho=0.9):
     """Lower Cholesky factor P of the precision of Sigma_ij = rho^|i-j|."""
-    idx = np.arange(d)
-    Sigma = rho ** np.abs(idx[:, None] - idx[None, :])
-    Q = np.linalg.inv(Sigma)
-    return np.linalg.cholesky((Q + Q.T) / 2)
+    # the AR(1) precision is tridiagonal: Q = (1-rho^2)^-1 * tridiag(-rho, [1, 1+rho^2, ..., 1+rho^2, 1], -rho);
+    # its Cholesky factor is exactly lower-bidiagonal
+    Q = np.zeros((d, d))
+    i = np.arange(d)
+    Q[i, i] = 1.0 + rho * rho
+    Q[0, 0] = Q[-1, -1] = 1.0
+    Q[i[1:], i[:-1]] = Q[i[:-1], i[1:]] = -rho
+    Q /= 1.0 - rho * rho
+    P = np.linalg.cholesky(Q)
+    P[np.abs(P) < 1e-14] = 0.0
+    return P

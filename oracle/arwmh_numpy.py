@@ -447,13 +447,25 @@ def ram_step(z, U, L, potential, normals, uniforms, n, lr_decay=2.0 / 3.0, targe
         acc = uniforms.astype(dt) < alpha
         z_new = np.where(acc[:, None], z_prop, z)
         U_new = np.where(acc, U_prop, U)
-        # eta_n <= 1 and alpha* < 1 keep 1 + eta (alpha - alpha*) > 0: the downdate stays PD
-        eta = dt.type(1.0) / dt.type(n) ** dt.type(lr_decay)
+        # Vihola (2012): eta_n = min(1, d n^-lr_decay); eta_n <= 1 and alpha* < 1 keep
+        # 1 + eta (alpha - alpha*) > 0, so the downdate stays positive definite
+        eta = min(dt.type(1.0), dt.type(z.shape[1]) / dt.type(n) ** dt.type(lr_decay))
         coef = eta * (alpha - dt.type(target_accept_prob)) / np.sum(normals.astype(dt) ** 2, axis=1)
         chol = cholesky_update(L, Lz, coef)
         bad = np.isnan(chol).any(axis=(1, 2))
         L_new = np.where(bad[:, None, None], L, chol)
     return z_new.astype(dt), U_new.astype(dt), L_new.astype(dt), alpha, acc
+
+
+def ram_run(z, U, L, potential, n_steps, draws, i0=0, record_accept=False, **kw):
+    """n_steps of ram_step with supplied draws (normals[T,C,d], uniforms[T,C]); n = iteration + 1."""
+    accs, zs = [], []
+    for t in range(n_steps):
+        z, U, L, _, acc = ram_step(z, U, L, potential, draws[0][t], draws[1][t], i0 + t + 1, **kw)
+        zs.append(z.copy())
+        if record_accept:
+            accs.append(acc.copy())
+    return z, U, L, dict(z=np.stack(zs), accepts=np.stack(accs) if record_accept else None)
 
 
 # --------------------------------------------------------------------------
