@@ -302,7 +302,26 @@ def run_ours(args):
         launches += K * max(1, -(-S_ // chunk_S))
 
     extra = None
-    if not args.no_extra:  # secondary workload: runs on every rank (it all-reduces)
+    thin1 = None
+    if not args.no_extra:
+        # SURVEY 8d config 3 asks for thinning 1 as well: every state is written (44 B per chain-step)
+        T1 = 1000
+        for _ in range(2):
+            sampler.run_batch(batch, T1, thinning=1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            sampler.run_batch(batch, T1, thinning=1)
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+        rate1 = world * Cn * T1 * 3 / (float(t1.item()) * 1e-3)
+        thin1 = {"value": rate1, "unit": "chain-steps/s", "fused_iterations_per_launch": T1,
+                 "sample_stream_GBps_per_gpu": rate1 / world * (d + 1) * esz / 1e9}
+    if not args.no_extra:  # secondary workloads: run on every rank (they all-reduce)
         del kept, zs, flush
         torch.cuda.empty_cache()
         extra = {}
@@ -372,6 +391,8 @@ def run_ours(args):
                      "peak = fallback 6650 GB/s (of fallback)"),
         },
     }
+    if thin1 is not None:
+        line["thinning_1"] = thin1
     if extra is not None:
         line["extra_workloads"] = extra
     if not args.no_cpu_baseline and world == 1:
@@ -400,7 +421,9 @@ def run_diamonds_tc(args, world, rank, dev, K, W):
     import adaptive_mcmc_b200 as am
     from adaptive_mcmc_b200.parallel import PooledARWMH
 
-    Cn, pool_every, windows = 65536, 100, 10
+    # 65,536 chains on one GPU is the configuration the tensor-pipe target is quoted on; BASELINE.json configs[3]
+    # (2^20 chains over 8 GPUs) is 131,072 per GPU: `--chains 131072`
+    Cn, pool_every, windows = (args.chains or 65536), 100, 10
     data = am.models.synthetic_diamonds(n=5000, k=25, seed=0)
     X, Y = data["X"], data["Y"]
     Xc = np.column_stack([np.ones(len(Y)), X[:, 1:] - X[:, 1:].mean(0)])
@@ -467,7 +490,7 @@ def run_diamonds_tc(args, world, rank, dev, K, W):
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     per_gpu = rate / world
     return {
-        "workload": "diamonds-diamonds synthetic (d=26, N=5000, Kc=24), 65,536 chains per GPU, pooled adaptation every 100 steps "
+        "workload": f"diamonds-diamonds synthetic (d=26, N=5000, Kc=24), {Cn:,} chains per GPU, pooled adaptation every 100 steps "
                     "(BASELINE.json configs[3] slice), tcgen05 split-bf16 likelihood",
         "metric": "chain-steps/sec", "value": rate, "unit": "chain-steps/s", "ms_per_step": ms / K,
         "fused_iterations_per_step": T, "windows_per_step": windows,
