@@ -256,6 +256,19 @@ def philox_words(seed, chain_ids, step, n_words):
     return out[:, :n_words]
 
 
+def box_muller_words(words):
+    """Box-Muller on consecutive word pairs (2k, 2k+1) in float32, exactly as the device does."""
+    wa = words[:, 0::2]
+    wb = words[:, 1::2]
+    u1 = wa.astype(np.float32) * np.float32(2.0**-32) + np.float32(2.0**-33)
+    th = np.float32(2.0 * math.pi) * (wb.astype(np.int32).astype(np.float32) * np.float32(2.0**-32))
+    r = np.sqrt(np.float32(-2.0) * np.log(u1))
+    z = np.empty((words.shape[0], 2 * wa.shape[1]), np.float32)
+    z[:, 0::2] = r * np.cos(th)
+    z[:, 1::2] = r * np.sin(th)
+    return z
+
+
 def words_to_draws(words, d, dt=np.float32):
     """Map Philox words to (normals[C,d], uniform[C]) exactly as the device does:
     Box-Muller on word pairs (2k, 2k+1) in float32:
