@@ -5,12 +5,12 @@ drivers that call it), built from hand-written sm_100a CUDA kernels behind a C A
 (``include/amcmc.h`` -> ``libamcmc.so``).  No CPU fallback, no Triton, no multi-backend dispatch.
 """
 from . import models
-from .kernels import ARWMH, RAM, ARWMHState, ARWMHAdaptState, ChainBatch, init_to_uniform, init_to_value
+from .kernels import ARWMH, RAM, ASSS, ASSSState, ASSSAdaptState, ARWMHState, ARWMHAdaptState, ChainBatch, init_to_uniform, init_to_value
 from .infer import MCMC
 from .utils.kernel_utils import ns_logscale, concat_trees, collect_states_logscale
 from . import diagnostics
 
 __all__ = [
-    "models", "ARWMH", "RAM", "ARWMHState", "ARWMHAdaptState", "ChainBatch", "init_to_uniform", "init_to_value",
+    "models", "ARWMH", "RAM", "ASSS", "ASSSState", "ASSSAdaptState", "ARWMHState", "ARWMHAdaptState", "ChainBatch", "init_to_uniform", "init_to_value",
     "MCMC", "ns_logscale", "concat_trees", "collect_states_logscale", "diagnostics",
 ]

@@ -201,7 +201,10 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
   if (rc) return rc;
   if (a->n_steps == 0) return AMCMC_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (a->kernel_kind != AMCMC_KERNEL_ARWMH && !(a->kernel_kind == AMCMC_KERNEL_RAM && m->model_id == AMCMC_MODEL_GAUSSIAN)) {
+  const bool small_family = m->model_id == AMCMC_MODEL_STD_NORMAL || m->model_id == AMCMC_MODEL_EIGHT_SCHOOLS ||
+                            m->model_id == AMCMC_MODEL_KIDIQ;
+  if (a->kernel_kind != AMCMC_KERNEL_ARWMH && !(a->kernel_kind == AMCMC_KERNEL_RAM && m->model_id == AMCMC_MODEL_GAUSSIAN) &&
+      !(a->kernel_kind == AMCMC_KERNEL_ASSS && small_family)) {
     set_error("amcmc_arwmh_run: kernel kind %d not available for model %d", a->kernel_kind, m->model_id);
     return AMCMC_ERR_UNSUPPORTED;
   }

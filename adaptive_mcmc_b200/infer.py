@@ -52,7 +52,7 @@ class MCMC:
         state = s.init(rng_key, self.num_warmup, init_params, model_args=args, model_kwargs=kwargs,
                        num_chains=self.num_chains)
         pot = s.potential
-        batch = ChainBatch.from_state(pot, state, copy=False)
+        batch = s._batch_from_state(state, copy=False)
         extra_fields = tuple(extra_fields)
         # numpyro.util.fori_collect: collection_size = num_samples // thinning, the first
         # (num_samples % thinning) post-warmup steps are skipped
@@ -102,7 +102,7 @@ class MCMC:
         if "z" in extra_fields:
             extras["z"] = self._z_unconstrained
         self._extra = extras
-        self._last_state = batch.to_state()
+        self._last_state = s._state_from_batch(batch)
         return self
 
     @staticmethod

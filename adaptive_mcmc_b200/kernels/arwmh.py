@@ -290,7 +290,7 @@ class ARWMH:
             )
         _lib.check(rc, "amcmc_arwmh_init")
         batch.i = 0
-        return batch.to_state()
+        return self._state_from_batch(batch)
 
     # ---- the fused run ----------------------------------------------------------
     def run_batch(self, batch: ChainBatch, num_steps, thinning=1, collect_start=0, collect=("z", "potential_energy"),
@@ -320,8 +320,9 @@ class ARWMH:
             nrm, uni = draws
             nrm = torch.as_tensor(nrm, **kw).contiguous()
             uni = torch.as_tensor(uni, **kw).contiguous()
-            if tuple(nrm.shape) != (T, batch.d, batch.C) or tuple(uni.shape) != (T, batch.C):
-                raise ValueError(f"draws must be normals[T,d,C]={T, batch.d, batch.C} and uniforms[T,C]; got "
+            want_n, want_u = self._draw_shapes(T, batch)
+            if tuple(nrm.shape) != want_n or tuple(uni.shape) != want_u:
+                raise ValueError(f"draws must be normals{want_n} and uniforms{want_u}; got "
                                  f"{tuple(nrm.shape)}, {tuple(uni.shape)}")
             a.rng_mode = _lib.RNG_EXTERNAL
             a.normals = nrm.data_ptr()
@@ -346,17 +347,32 @@ class ARWMH:
         batch.i = int(st.i)
         return out
 
+    def _draw_shapes(self, T, batch):
+        """Device layout of the external draws: normals[T, d, C], uniforms[T, C]."""
+        return (T, batch.d, batch.C), (T, batch.C)
+
+    def _batch_from_state(self, state, copy=True):
+        return ChainBatch.from_state(self._potential_fn, state, copy=copy)
+
+    def _state_from_batch(self, batch):
+        return batch.to_state()
+
+    def _draws_to_device_layout(self, draws):
+        """chain-major (normals[T,C,d], uniforms[T,C]) -> device layout."""
+        pot = self._potential_fn
+        nrm, uni = draws
+        nrm = torch.as_tensor(nrm, dtype=pot.dtype, device=pot.device).permute(0, 2, 1).contiguous()
+        return nrm, uni
+
     def run(self, state, num_steps, thinning=1, collect_start=0, collect=("z", "potential_energy"), draws=None,
             record_accept=False):
         """K fused ARWMH.sample steps.  Returns (collected, last_state); collected leaves are
         [S, C, ...] like numpyro.util.fori_collect over vectorised chains (draws, if given, are
         (normals[T,C,d], uniforms[T,C]) chain-major like the state)."""
         pot = self._potential_fn
-        batch = ChainBatch.from_state(pot, state, copy=True)
+        batch = self._batch_from_state(state, copy=True)
         if draws is not None:
-            nrm, uni = draws
-            nrm = torch.as_tensor(nrm, dtype=pot.dtype, device=pot.device).permute(0, 2, 1).contiguous()
-            draws = (nrm, uni)
+            draws = self._draws_to_device_layout(draws)
         raw = self.run_batch(batch, num_steps, thinning, collect_start, collect, draws, record_accept)
         coll = OrderedDict()
         if "z" in raw:
@@ -365,7 +381,7 @@ class ARWMH:
             coll["potential_energy"] = raw["potential_energy"]
         if "accept" in raw:
             coll["accept"] = raw["accept"].bool()
-        return coll, batch.to_state()
+        return coll, self._state_from_batch(batch)
 
     def sample(self, state, model_args=(), model_kwargs=None):
         """

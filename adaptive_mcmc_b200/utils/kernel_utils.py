@@ -59,7 +59,7 @@ def collect_states_logscale(rng_key, sampler, model_data: dict, n_pow=6):
     followed by a device-side snapshot.  Returned leaves are [len(grid), C, ...]; `z` stays
     unconstrained as in the reference (:36 is commented out there)."""
     last_state = sampler.init(rng_key, num_warmup=0, init_params={}, model_args=(), model_kwargs=model_data)
-    batch = ChainBatch.from_state(sampler.potential, last_state, copy=True)
+    batch = sampler._batch_from_state(last_state, copy=True)
     collections = []
     for p in range(n_pow + 1):
         lower_idx = 0 if p < 1 else 10 ** (p - 1)

@@ -325,7 +325,7 @@ def run_ours(args):
         del kept, zs, flush
         torch.cuda.empty_cache()
         extra = {}
-        for name, fn in (("diamonds_tc", run_diamonds_tc), ("gaussian_ram", run_gaussian_ram)):
+        for name, fn in (("diamonds_tc", run_diamonds_tc), ("gaussian_ram", run_gaussian_ram), ("asss_eight_schools", run_asss)):
             try:
                 extra[name] = fn(args, world, rank, dev, max(3, K // 2), 2)
             except Exception as e:  # the headline line must survive a failure of a secondary workload
@@ -560,6 +560,42 @@ def run_gaussian_ram(args, world, rank, dev, K, W):
                      "note": "algorithmic bytes = 2*4*(d(d+1)/2+2d+3) = 164,024 per chain-step (state round trip, SURVEY 8d); the "
                              "factor stays in shared memory for the 100 fused steps, so real HBM traffic is ~1/100 of that"},
     }
+
+
+# ------------------------------------------------------------------------------------------------
+# ASSS (python/kernels/asss.py; SURVEY 8f "next" row) on eight_schools
+# ------------------------------------------------------------------------------------------------
+def run_asss(args, world, rank, dev, K, W):
+    import torch
+    import torch.distributed as dist
+
+    import adaptive_mcmc_b200 as am
+
+    Cn, T = 65536, 2000
+    s = am.ASSS(am.models.eight_schools, num_chains=Cn, device=dev, chain_offset=rank * Cn)
+    st = s.init(0, num_warmup=W * T, init_params=None)
+    b = s._batch_from_state(st, copy=False)
+    for _ in range(W):
+        s.run_batch(b, T, thinning=25)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if world > 1:
+        dist.barrier()
+    for k in range(K):
+        flush.fill_(k & 0xFF)
+        ev[k][0].record()
+        s.run_batch(b, T, thinning=25)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(c) for a, c in ev)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"workload": "eight_schools d=10, adaptive stereographic slice sampler (python/kernels/asss.py), 65,536 chains per GPU, "
+                        "2,000 fused steps per launch, thinning 25 (the reference's ASSS thinning)",
+            "metric": "chain-steps/sec", "value": world * Cn * T * K / (ms * 1e-3), "unit": "chain-steps/s", "ms_per_step": ms / K,
+            "mean_shrink_iterations": float(b.macc.mean()), "gpu_launches": K}
 
 
 def _traffic(key):

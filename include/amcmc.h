@@ -55,8 +55,11 @@ enum amcmc_rng_mode {
   AMCMC_RNG_EXTERNAL = 1  /* caller supplies normals[T][d][C] and uniforms[T][C] (shared-draw parity mode) */
 };
 
-/* Sampler variants (arwmh.py is AMCMC_KERNEL_ARWMH; RAM is BASELINE.json config 5, not in the reference). */
-enum amcmc_kernel_kind { AMCMC_KERNEL_ARWMH = 0, AMCMC_KERNEL_RAM = 1 };
+/* Sampler variants: AMCMC_KERNEL_ARWMH = python/kernels/arwmh.py; AMCMC_KERNEL_RAM = BASELINE.json configs[4]
+ * (not in the reference); AMCMC_KERNEL_ASSS = python/kernels/asss.py:192-269, the adaptive stereographic slice
+ * sampler (state: log_step_size unused, mean_accept_prob carries the mean number of shrinkage iterations;
+ * external draws: normals[T][d+1][C], uniforms[T][52][C] = u_t, theta_0/2pi, 50 shrinkage draws). */
+enum amcmc_kernel_kind { AMCMC_KERNEL_ARWMH = 0, AMCMC_KERNEL_RAM = 1, AMCMC_KERNEL_ASSS = 2 };
 
 typedef struct amcmc_model amcmc_model; /* opaque: device copies of the model data */
 

@@ -4,6 +4,7 @@
 // It is never built by __graft_entry__.build(), never loaded by the adaptive_mcmc_b200 package and
 // is not a fallback: the product path has no CPU implementation.
 #include "../../adaptive_mcmc_b200/csrc/arwmh_small.cuh"
+#include "../../adaptive_mcmc_b200/csrc/asss_small.cuh"
 
 using namespace amcmc;
 
@@ -38,3 +39,22 @@ static void run_es(const double* y, const double* sigma, double cst, int64_t C, 
 
 extern "C" void hostsim_es_f32(ARGS(float)) { run_es<float>(PASS); }
 extern "C" void hostsim_es_f64(ARGS(double)) { run_es<double>(PASS); }
+
+template <typename R>
+static void run_es_asss(const double* y, const double* sigma, double cst, int64_t C, R* z, R* pe, R* macc, R* loc, R* scale,
+                        R* lam, R* asc, int64_t i0, int64_t n_steps, int64_t thinning, int64_t collect_start,
+                        int64_t num_warmup, double lr, double target, double eps, uint64_t seed, int64_t chain_offset,
+                        const R* normals, const R* uniforms, R* out_z, R* out_pe, uint8_t* out_acc, int adapt) {
+  EightSchoolsModel<R> m;
+  for (int j = 0; j < 8; ++j) { m.y[j] = (R)y[j]; m.inv_sigma[j] = (R)(1.0 / sigma[j]); }
+  m.cst = (R)cst;
+  StateView<R> st{C, z, pe, macc, loc, scale, lam, asc};
+  RunView<R> a{i0, n_steps, thinning, collect_start, num_warmup, (R)lr, (R)target, (R)eps, seed, chain_offset,
+               normals, uniforms, out_z, out_pe, out_acc};
+  for (int64_t c = 0; c < C; ++c) {
+    if (normals) asss_chain_run<EightSchoolsModel<R>, R, true>(m, st, a, c);
+    else asss_chain_run<EightSchoolsModel<R>, R, false>(m, st, a, c);
+  }
+}
+extern "C" void hostsim_es_asss_f32(ARGS(float)) { run_es_asss<float>(PASS); }
+extern "C" void hostsim_es_asss_f64(ARGS(double)) { run_es_asss<double>(PASS); }

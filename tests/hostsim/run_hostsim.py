@@ -15,7 +15,7 @@ def es_cst(sigma):
 
 
 def run_es(state, n_steps, draws=None, seed=0, chain_offset=0, thinning=1, collect_start=0, num_warmup=0,
-           lr_decay=2 / 3, target=0.234, eps=1e-6, adapt=True, y=None, sigma=None):
+           lr_decay=2 / 3, target=0.234, eps=1e-6, adapt=True, y=None, sigma=None, kernel="arwmh"):
     from oracle.arwmh_numpy import ARWMHAdaptState, ARWMHState, EIGHT_SCHOOLS_SIGMA, EIGHT_SCHOOLS_Y
     lib = C.CDLL(os.path.join(_HERE, "libhostsim.so"))
     y = EIGHT_SCHOOLS_Y if y is None else np.asarray(y, np.float64)
@@ -26,16 +26,21 @@ def run_es(state, n_steps, draws=None, seed=0, chain_offset=0, thinning=1, colle
     z = np.ascontiguousarray(state.z.T).copy()
     loc = np.ascontiguousarray(state.adapt_state.loc.T).copy()
     scale = np.ascontiguousarray(state.adapt_state.scale[:, ii, jj].T).copy()
-    pe = state.potential_energy.copy(); macc = state.mean_accept_prob.copy()
-    lam = state.adapt_state.log_step_size.copy(); asc = state.as_change.copy()
+    pe = state.potential_energy.copy(); asc = state.as_change.copy()
+    macc = state.mean_accept_prob.copy() if hasattr(state, "mean_accept_prob") else np.zeros(Cn, dt)
+    lam = state.adapt_state.log_step_size.copy() if hasattr(state.adapt_state, "log_step_size") else np.zeros(Cn, dt)
     S = max(0, (n_steps - collect_start) // thinning)
     out_z = np.zeros((S, d, Cn), dt); out_pe = np.zeros((S, Cn), dt); out_acc = np.zeros((n_steps, Cn), np.uint8)
     nrm = uni = None
     if draws is not None:
         nrm = np.ascontiguousarray(np.transpose(draws[0], (0, 2, 1)).astype(dt))
-        uni = np.ascontiguousarray(draws[1].astype(dt))
+        uni = np.ascontiguousarray(draws[1].astype(dt)) if kernel != "asss" else \
+            np.ascontiguousarray(np.transpose(draws[1], (0, 2, 1)).astype(dt))
     p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
-    f = lib.hostsim_es_f64 if dt == np.float64 else lib.hostsim_es_f32
+    if kernel == "asss":
+        f = lib.hostsim_es_asss_f64 if dt == np.float64 else lib.hostsim_es_asss_f32
+    else:
+        f = lib.hostsim_es_f64 if dt == np.float64 else lib.hostsim_es_f32
     f.restype = None
     f(p(y), p(sigma), C.c_double(es_cst(sigma)), C.c_int64(Cn), p(z), p(pe), p(macc), p(loc), p(scale), p(lam), p(asc),
       C.c_int64(state.i), C.c_int64(n_steps), C.c_int64(thinning), C.c_int64(collect_start), C.c_int64(num_warmup),
