@@ -259,3 +259,37 @@ def test_reference_binding_example():
     assert abs(float(z[..., 0].mean()) - 4.4) < 0.5
     with pytest.raises(ValueError):
         mod.B200ARWMH("eight_schools", num_chains=4, y=[1.0], sigma=[1.0])
+
+
+def test_odd_sizes_all_kernels():
+    """Ragged chain counts / dimensions (not multiples of the CTA or warp size) through every kernel family:
+    results finite, shapes right (compute-sanitizer is closed on this pool, so boundary handling is checked here)."""
+    g = torch.Generator().manual_seed(0)
+    for dt in (torch.float32, torch.float64):
+        s = am.ARWMH(models.eight_schools, num_chains=97, dtype=dt)
+        st = s.init(1, num_warmup=5, init_params=None)
+        c, st = s.run(st, 23, thinning=3, collect_start=2, record_accept=True)
+        assert c["z"]["theta_base"].shape == (7, 97, 8) and c["accept"].shape == (23, 97)
+        c, st = s.run(st, 7, draws=(torch.randn(7, 97, 10, generator=g), torch.rand(7, 97, generator=g)))
+        assert torch.isfinite(st.adapt_state.scale).all() and int(st.i) == 30
+        a = am.ASSS(models.eight_schools, num_chains=33, dtype=dt)
+        sa = a.init(2, num_warmup=0, init_params=None)
+        c, sa = a.run(sa, 11, thinning=2)
+        c, sa = a.run(sa, 5, draws=(torch.randn(5, 33, 11, generator=g), torch.rand(5, 33, 52, generator=g)))
+        assert torch.isfinite(sa.potential_energy).all() and c["z"]["mu"].shape == (5, 33)
+        k = am.ARWMH(models.kidiq, num_chains=19, dtype=dt)
+        sk = k.init(3, num_warmup=0, init_params=None, model_kwargs=models.synthetic_kidiq())
+        c, sk = k.run(sk, 9)
+        assert torch.isfinite(sk.adapt_state.scale).all()
+        d = am.ARWMH(models.diamonds, num_chains=5, dtype=dt)
+        sd = d.init(4, num_warmup=0, init_params=None, model_kwargs=models.synthetic_diamonds(n=777))
+        c, sd = d.run(sd, 6, thinning=2)
+        assert c["z"]["b"].shape == (3, 5, 24) and torch.isfinite(sd.adapt_state.scale).all()
+        r = am.RAM(models.gaussian, num_chains=3, dtype=dt, init_strategy=am.init_to_value(torch.zeros(3, 37)))
+        sr = r.init(5, num_warmup=0, init_params=None, model_kwargs=dict(prec_chol=models.ar1_precision_chol(37, 0.5)))
+        c, sr = r.run(sr, 8, thinning=4)
+        c, sr = r.run(sr, 4, draws=(torch.randn(4, 3, 37, generator=g), torch.rand(4, 3, generator=g)))
+        assert torch.isfinite(sr.adapt_state.scale).all() and c["z"]["x"].shape == (4, 3, 37)
+        n = am.ARWMH(potential_fn=models.std_normal.bind(d=1, dtype=dt))
+        out = n.sample_Pnx(0, torch.zeros(7, 1), am.ARWMHAdaptState(torch.zeros(1), torch.eye(1), torch.tensor(0.0)), n=3, n_samples=5)
+        assert out.shape == (7, 5, 1) and torch.isfinite(out).all()

@@ -61,3 +61,30 @@ def test_missing_library_fails_loudly(monkeypatch):
 def test_cpu_device_rejected():
     with pytest.raises((ValueError, RuntimeError, AssertionError)):
         am.models.eight_schools.bind(device="cpu")
+
+
+def test_save_states_in_reference_pickle_format(tmp_path):
+    """a collected state tree pickles under the reference's class paths with NumPy leaves."""
+    import pickle, sys, types
+    from collections import namedtuple, OrderedDict
+    from adaptive_mcmc_b200.utils.io import save_states
+    S, C, d = 5, 3, 4
+    st = K.ARWMHState(torch.arange(1, S + 1), OrderedDict(mu=torch.randn(S, C), theta=torch.randn(S, C, 2)), torch.randn(S, C),
+                      torch.rand(S, C), K.ARWMHAdaptState(torch.randn(S, C, d), torch.randn(S, C, d, d), torch.randn(S, C)),
+                      torch.rand(S, C), torch.zeros(S, 2, dtype=torch.int64))
+    p = tmp_path / "run0.pkl"
+    save_states(st, str(p), chain=1)
+    assert "kernels.arwmh" not in sys.modules  # the stub modules are gone after the dump
+    # the reference environment: python/kernels/arwmh.py defines the record types
+    kern = types.ModuleType("kernels"); arw = types.ModuleType("kernels.arwmh")
+    arw.ARWMHState = namedtuple("ARWMHState", K.ARWMHState._fields); arw.ARWMHState.__module__ = "kernels.arwmh"
+    arw.ARWMHAdaptState = namedtuple("ARWMHAdaptState", K.ARWMHAdaptState._fields); arw.ARWMHAdaptState.__module__ = "kernels.arwmh"
+    sys.modules["kernels"], sys.modules["kernels.arwmh"] = kern, arw
+    try:
+        got = pickle.load(open(p, "rb"))
+    finally:
+        del sys.modules["kernels"], sys.modules["kernels.arwmh"]
+    assert type(got) is arw.ARWMHState and type(got.adapt_state) is arw.ARWMHAdaptState
+    assert got.potential_energy.shape == (S,) and got.adapt_state.scale.shape == (S, d, d) and got.z["theta"].shape == (S, 2)
+    np.testing.assert_array_equal(got.potential_energy, st.potential_energy[:, 1].numpy())
+    np.testing.assert_array_equal(got.i, np.arange(1, S + 1))
