@@ -85,11 +85,6 @@ template <typename R, int D> AMCMC_HD R factor_frob2(const ChainRegs<R, D>& s) {
   return ss;
 }
 
-struct StepConsts {
-  // filled per step (chain-independent)
-  bool n_is_one;
-};
-
 // One ARWMH.sample (python/kernels/arwmh.py:140-207) for the chain held in `s`.
 template <class Model, typename R, bool ADAPT>
 AMCMC_HD bool arwmh_step(ChainRegs<R, Model::D>& s, const Model& m, const R (&z)[Model::D], R u, R nf,
