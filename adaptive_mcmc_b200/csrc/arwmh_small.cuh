@@ -94,13 +94,16 @@ AMCMC_HD bool arwmh_step(ChainRegs<R, Model::D>& s, const Model& m, const R (&z)
   // :166-167  x' = x + (L e^lam + eps I) z,  L z = Lt (sqrt(Dg) .* z)
   R y[D], xp[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) y[j] = z[j] * Num<R>::sqrt(s.Dg[j]);
+  for (int j = 0; j < D; ++j) {
+    y[j] = z[j] * Num<R>::sqrt(s.Dg[j]);
+    xp[j] = fma(eps, z[j], s.x[j]);  // the eps I z term is folded in here so that z dies before the matvec
+  }
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     R acc = y[i];
 #pragma unroll
     for (int j = 0; j < i; ++j) acc = fma(s.Lt[tri_strict(i, j)], y[j], acc);
-    xp[i] = s.x[i] + fma(el, acc, eps * z[i]);
+    xp[i] = fma(el, acc, xp[i]);
   }
   // :170-171
   R Up = m.potential(xp);
@@ -118,14 +121,17 @@ AMCMC_HD bool arwmh_step(ChainRegs<R, Model::D>& s, const Model& m, const R (&z)
   // :183, :188-193
   const R gamma = n_is_one ? (R)1 : Num<R>::pow_neg(nf, lr_decay);
   R w[D];
-  bool ok = !n_is_one;
+  // pre-condition of the sweep in two comparisons: sum |delta| finite and below kBig, min D > 0
+  R dabs = 0, dmin = s.Dg[0];
 #pragma unroll
   for (int k = 0; k < D; ++k) {
     const R dl = s.x[k] - s.mu[k];
     s.mu[k] = fma(gamma, dl, s.mu[k]);
     w[k] = dl;
-    ok = ok && (Num<R>::abs(dl) < Num<R>::kBig) && (s.Dg[k] > (R)0);
+    dabs += Num<R>::abs(dl);
+    dmin = s.Dg[k] < dmin ? s.Dg[k] : dmin;
   }
+  const bool ok = !n_is_one && (dabs < Num<R>::kBig) && (dmin > (R)0);
   const R lam_new = fma(gamma, alpha - target, s.lam);
   // :190-191 rank-one update; "NaN => keep the old factor" is applied as a pre-condition
   // (gamma == 1 <=> zero scaled diagonal, non-positive pivot, non-finite delta), see DESIGN.md.

@@ -33,6 +33,16 @@ template <> struct Num<float> {
     return ::logf(x);
 #endif
   }
+  // ln(x) for x known to be a NORMAL positive float (no denormal fix-up sequence): one MUFU.LG2 + one FMUL
+  static AMCMC_HD float log_normal_range(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * 0.6931471805599453f;
+#else
+    return ::logf(x);
+#endif
+  }
   static AMCMC_HD float log1p(float x) { return ::log1pf(x); }
   static AMCMC_HD float rcp(float x) {
 #ifdef __CUDA_ARCH__
@@ -56,7 +66,10 @@ template <> struct Num<float> {
   // n^(-p) for n >= 1
   static AMCMC_HD float pow_neg(float n, float p) {
 #ifdef __CUDA_ARCH__
-    return exp2f(-p * __log2f(n));
+    float l, r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(n));   // n >= 1: normal range, lg2(1) == 0 exactly
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-p * l));
+    return r;
 #else
     return 1.0f / ::powf(n, p);
 #endif
@@ -130,7 +143,7 @@ AMCMC_HD void box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1) {
   float u1 = fmaf((float)wa, 0x1p-32f, 0x1p-33f);
   float th = 6.283185307179586f * ((float)(int32_t)wb * 0x1p-32f);
 #ifdef __CUDA_ARCH__
-  float r = Num<float>::sqrt(-2.0f * __logf(u1));
+  float r = Num<float>::sqrt(-2.0f * Num<float>::log_normal_range(u1));  // u1 >= 2^-33: never denormal
   float s, c;
   __sincosf(th, &s, &c);
 #else
