@@ -219,7 +219,8 @@ AMCMC_HD void asss_chain_run(const Model& m, const StateView<R>& st, const RunVi
 
 #ifdef __CUDACC__
 template <class Model, typename R, bool EXTERNAL>
-__global__ void __launch_bounds__(64, (sizeof(R) == 4 ? 6 : 1))
+// 7 resident CTAs of 64 threads per SM (128 registers): 65,536 chains fit in ONE wave, as for arwmh_small_kernel
+__global__ void __launch_bounds__(64, (sizeof(R) == 4 ? 7 : 1))
 asss_small_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st.C) return;
