@@ -50,69 +50,63 @@ template <typename R, int NT> __device__ __forceinline__ R block_inclusive_scan(
   return v + add;
 }
 
-constexpr int kRamThreads = 512;  // two threads per row of the factor (row split at its midpoint)
+constexpr int kRamThreads = 512;  // two threads per row of the factor (row split at its middle 4-column chunk)
+
+// ---- storage of the unit factor: ROW-major, 4-column chunks, rows padded so that 128-bit accesses of a warp
+// (32 consecutive rows, each at its own right-to-left position) fall into distinct bank groups:
+// the END chunk of consecutive rows advances by exactly one 4-element unit modulo 8.
+AMCMC_HD int ram_nq(int i) { return (i + 3) >> 2; }  // 4-column chunks of row i (columns 0..i-1)
+AMCMC_HD int ram_row_units(int i) {
+  const int q = ram_nq(i), want = (1 - (ram_nq(i + 1) - q)) & 7;  // units(i) == want (mod 8), units(i) >= max(q, 1)
+  const int base = q > 0 ? q : 1;
+  return base + ((want - base) & 7);
+}
+AMCMC_HD int ram_total_units(int d) {
+  int t = 0;
+  for (int i = 0; i < d; ++i) t += ram_row_units(i);
+  return t;
+}
+
+template <typename R> struct alignas(4 * sizeof(R) > 16 ? 16 : 4 * sizeof(R)) RVec4 { R a, b, c, e; };
 
 // Shared-memory carve-up of the RAM kernel
 template <typename R> struct RamSmem {
-  R *x, *xp, *Dg, *v, *y, *part0, *part1, *red, *scal, *Lt;
-  float4* pk;  // per column j: (beta_j, p_j of this step, p_j of the NEXT step, unused)  -- one 16-byte broadcast load
+  R *beta, *pj, *pn;  // per-column parameters of the walk (chunk q = four consecutive columns = one vector load)
+  R *x, *xp, *Dg, *v, *part0, *part1, *red, *scal, *Lt;
+  int* rb;            // row base (in 4-element units) of every row
   __device__ RamSmem(unsigned char* base, int d) {
-    const int dp = (d + 3) & ~3;
-    pk = reinterpret_cast<float4*>(base);
-    R* p = reinterpret_cast<R*>(base + sizeof(R) * 4 * dp);
-    x = p; p += dp; xp = p; p += dp; Dg = p; p += dp; v = p; p += dp; y = p; p += dp;
-    part0 = p; p += dp; part1 = p; p += dp; red = p; p += 32; scal = p; p += 8;
+    const int dp = ((d + 3) & ~3) + 4;
+    R* p = reinterpret_cast<R*>(base);
+    beta = p; p += dp; pj = p; p += dp; pn = p; p += dp;
+    x = p; p += dp; xp = p; p += dp; Dg = p; p += dp; v = p; p += dp; part0 = p; p += dp; part1 = p; p += dp;
+    red = p; p += 32; scal = p; p += 8;
+    rb = reinterpret_cast<int*>(p); p += (dp * sizeof(int) + sizeof(R) - 1) / sizeof(R);
+    p = reinterpret_cast<R*>((reinterpret_cast<uintptr_t>(p) + 31) & ~(uintptr_t)31);
     Lt = p;
   }
   static size_t bytes(int d) {
-    const int dp = (d + 3) & ~3;
-    return sizeof(R) * ((size_t)11 * dp + 40 + (size_t)d * (d - 1) / 2 + 4);
+    const int dp = ((d + 3) & ~3) + 4;
+    return sizeof(R) * ((size_t)10 * dp + 40 + 8 + (size_t)4 * ram_total_units(d)) + 64;
   }
 };
 
-// One fused pass over the column-major packed unit factor per MCMC step.  Thread (row i, segment) walks its
-// half row right to left; ALL lanes of a warp visit the same column j together (consecutive rows of a column
-// are contiguous in the packed layout => conflict-free, and the per-column parameters are one broadcast
-// 16-byte load).  For every element:
+// One fused pass over the factor per MCMC step.  Thread (row i, segment) walks its half row RIGHT TO LEFT in
+// 4-column chunks (one 128-bit load + one 128-bit store of the row, three 128-bit loads of the column parameters):
 //     Lt_ij' = Lt_ij + beta_j w          (rank-one update; w = running suffix sum_{k>j}^{i} Lt_ik p_k)
 //     w     += Lt_ij p_j
 //     acc   += Lt_ij' p_j^next           (row sum of the NEXT proposal  v^next = Lt' p^next)
 // so the factor is read once and written once per step (160 KB of SMEM traffic at d = 200, fp32).
-template <typename R> struct RamPk { R beta, pj, pn, pad; };
-
-template <typename R, bool PRED>
-__device__ __forceinline__ void ram_walk(R* __restrict__ Lt, const R* pk4, int d, int row, int j_from, int j_to,
-                                         int j_lo, int j_hi, R& w, R& acc) {
-  // visits j = j_from-1, ..., j_to (descending); pk4 is the packed per-column parameter array (4 values each)
-  const RamPk<R>* pk = reinterpret_cast<const RamPk<R>*>(pk4);
-  int j = j_from - 1;
-  int ad = colbase(j, d) + row - j - 1;  // address of (row, j); (row, j-1) sits d - 1 - j lower
-  if (!PRED) {
-    // four columns per trip: the four loads are issued before any store so that their latency overlaps
-    for (; j - 3 >= j_to; j -= 4) {
-      const int a0 = ad, a1 = a0 - (d - 1 - j), a2 = a1 - (d - j), a3 = a2 - (d + 1 - j);
-      const R L0 = Lt[a0], L1 = Lt[a1], L2 = Lt[a2], L3 = Lt[a3];
-      const RamPk<R> p0 = pk[j], p1 = pk[j - 1], p2 = pk[j - 2], p3 = pk[j - 3];
-      const R n0 = fma(p0.beta, w, L0); w = fma(L0, p0.pj, w);
-      const R n1 = fma(p1.beta, w, L1); w = fma(L1, p1.pj, w);
-      const R n2 = fma(p2.beta, w, L2); w = fma(L2, p2.pj, w);
-      const R n3 = fma(p3.beta, w, L3); w = fma(L3, p3.pj, w);
-      Lt[a0] = n0; Lt[a1] = n1; Lt[a2] = n2; Lt[a3] = n3;
-      acc = fma(n0, p0.pn, acc); acc = fma(n1, p1.pn, acc); acc = fma(n2, p2.pn, acc); acc = fma(n3, p3.pn, acc);
-      ad = a3 - (d + 2 - j);
-    }
-  }
-  for (; j >= j_to; --j) {
-    if (!PRED || (j >= j_lo && j < j_hi)) {
-      const R Lo = Lt[ad];
-      const RamPk<R> p = pk[j];
-      const R Ln = fma(p.beta, w, Lo);
-      Lt[ad] = Ln;
-      w = fma(Lo, p.pj, w);
-      acc = fma(Ln, p.pn, acc);
-    }
-    ad -= d - 1 - j;
-  }
+template <typename R, bool MASK>
+__device__ __forceinline__ void ram_chunk(RVec4<R>* Lrow, const RVec4<R>* b4, const RVec4<R>* p4, const RVec4<R>* n4,
+                                          int q, int row, R& w, R& acc) {
+  RVec4<R> L = Lrow[q];
+  const RVec4<R> B = b4[q], P = p4[q], N = n4[q];
+  const int j0 = 4 * q;
+  if (!MASK || j0 + 3 < row) { const R n = fma(B.e, w, L.e); w = fma(L.e, P.e, w); acc = fma(n, N.e, acc); L.e = n; }
+  if (!MASK || j0 + 2 < row) { const R n = fma(B.c, w, L.c); w = fma(L.c, P.c, w); acc = fma(n, N.c, acc); L.c = n; }
+  if (!MASK || j0 + 1 < row) { const R n = fma(B.b, w, L.b); w = fma(L.b, P.b, w); acc = fma(n, N.b, acc); L.b = n; }
+  { const R n = fma(B.a, w, L.a); w = fma(L.a, P.a, w); acc = fma(n, N.a, acc); L.a = n; }
+  Lrow[q] = L;
 }
 
 template <class BM, typename R, bool EXTERNAL>
@@ -121,45 +115,38 @@ __global__ void __launch_bounds__(kRamThreads, 2) ram_block_kernel(const BM m, c
   constexpr int NT = kRamThreads;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RamSmem<R> sm(smem_raw, d);
-  R* pk4 = reinterpret_cast<R*>(sm.pk);
   const int tid = threadIdx.x;
   const int seg = tid >> 8, row = tid & 255;
   const bool has_row = row < d;
-  const int j_lo = has_row ? (seg == 0 ? 0 : row / 2) : 0;
-  const int j_hi = has_row ? (seg == 0 ? row / 2 : row) : 0;  // [j_lo, j_hi)
-  // warp-uniform loop bounds: union [u_lo, u_hi) and common part [c_lo, c_hi) of the lanes' segments
-  int u_lo = (j_hi > j_lo) ? j_lo : 0x7fffffff, u_hi = (j_hi > j_lo) ? j_hi : 0;
-  int c_lo = has_row ? j_lo : 0, c_hi = has_row ? j_hi : 0x7fffffff;  // rows beyond d do not constrain the common part
-  if (!has_row) c_lo = 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    u_lo = min(u_lo, __shfl_xor_sync(0xffffffffu, u_lo, o));
-    u_hi = max(u_hi, __shfl_xor_sync(0xffffffffu, u_hi, o));
-    c_lo = max(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o));
-    c_hi = min(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o));
-  }
-  if (u_hi <= u_lo) { u_lo = 0; u_hi = 0; }
-  // a warp containing out-of-range rows (row >= d) keeps everything predicated
-  const bool all_rows = __all_sync(0xffffffffu, has_row);
-  if (!all_rows || c_hi <= c_lo) { c_lo = u_lo; c_hi = u_lo; }  // empty common part
-  c_hi = min(c_hi, u_hi);
-  c_lo = max(c_lo, u_lo);
+  // this thread's chunks of row `row`: seg 1 = [qs, nq), seg 0 = [0, qs)
+  const int nq = has_row ? ram_nq(row) : 0;
+  const int qs = nq >> 1;
+  const int q_hi = (seg == 1) ? nq : qs, q_lo = (seg == 1) ? qs : 0;
+  int rbase = 0;
+  for (int k = 0; k < row && k < d; ++k) rbase += ram_row_units(k);
+  if (seg == 0 && has_row) sm.rb[row] = rbase;
+  RVec4<R>* Lrow = reinterpret_cast<RVec4<R>*>(sm.Lt) + rbase;
+  const RVec4<R>* b4 = reinterpret_cast<const RVec4<R>*>(sm.beta);
+  const RVec4<R>* p4 = reinterpret_cast<const RVec4<R>*>(sm.pj);
+  const RVec4<R>* n4 = reinterpret_cast<const RVec4<R>*>(sm.pn);
 
   const int64_t C = st.C, c = blockIdx.x;
-  // ---- load: L (row-major packed with diagonal) -> Lt column-major packed, Dg
+  // ---- load: L (row-major packed with diagonal) -> unit factor in the padded row layout, Dg
   for (int k = tid; k < d; k += NT) {
     sm.x[k] = st.z[k * C + c];
     const R dg = st.scale[(int64_t)tri_full(k, k) * C + c];
     sm.Dg[k] = dg * dg;
-    sm.y[k] = (R)1 / dg;
+    sm.v[k] = (R)1 / dg;
   }
+  const int lt_floats = 4 * ram_total_units(d);
+  for (int k = tid; k < lt_floats; k += NT) sm.Lt[k] = 0;  // padding must be finite
   __syncthreads();
   for (int e = tid; e < d * (d - 1) / 2; e += NT) {
     int i = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)e)) * 0.5f);
     while (i * (i - 1) / 2 > e) --i;
     while ((i + 1) * i / 2 <= e) ++i;
     const int j = e - i * (i - 1) / 2;
-    sm.Lt[cm_idx(i, j, d)] = st.scale[(int64_t)tri_full(i, j) * C + c] * sm.y[j];
+    sm.Lt[4 * sm.rb[i] + j] = st.scale[(int64_t)tri_full(i, j) * C + c] * sm.v[j];
   }
   R U = st.pe[c], macc = st.macc[c];
   __syncthreads();
@@ -191,18 +178,28 @@ __global__ void __launch_bounds__(kRamThreads, 2) ram_block_kernel(const BM m, c
     }
   };
 
-  // per-thread (tid < d) registers describing the CURRENT step's draw: z_j, z_j^2, prefix sum, |z|^2 in scal[2]
+  // the fused walk of this thread's half row; returns the row-sum contribution of the NEXT proposal
+  auto walk = [&](R w) -> R {
+    R acc = 0;
+    int q = q_hi - 1;
+    if (q >= q_lo && seg == 1) { ram_chunk<R, true>(Lrow, b4, p4, n4, q, row, w, acc); --q; }  // ragged right end
+    for (; q >= q_lo; --q) ram_chunk<R, false>(Lrow, b4, p4, n4, q, row, w, acc);
+    return acc;
+  };
+
+  // per-thread (tid < d) registers describing the CURRENT step's draw: z_j, z_j^2, prefix sum; |z|^2 in scal[2]
   R zj = 0, zsq = 0, pref = 0;
   // ---- prologue: draws of step 0, p^0 = sqrt(D) z^0, and one walk with beta = 0 to get v^0 = Lt p^0
   draw(0, a.i0, 0);
   __syncthreads();
+  for (int k = tid; k < ((d + 3) & ~3) + 4; k += NT) { sm.beta[k] = 0; sm.pj[k] = 0; }
   if (tid < d) {
     zj = sm.v[tid];
     zsq = zj * zj;
-    pk4[4 * tid] = 0;                                      // beta
-    pk4[4 * tid + 1] = 0;                                  // p of a (non-existent) previous step
-    pk4[4 * tid + 2] = zj * Num<R>::sqrt(sm.Dg[tid]);      // p^0
+    sm.pn[tid] = zj * Num<R>::sqrt(sm.Dg[tid]);  // p^0
     sm.part1[tid] = 0;
+  } else if (tid < ((d + 3) & ~3) + 4) {
+    sm.pn[tid] = 0;
   }
   pref = block_inclusive_scan<R, NT>(zsq, sm.red);
   if (tid == d - 1) sm.scal[2] = pref;
@@ -210,13 +207,10 @@ __global__ void __launch_bounds__(kRamThreads, 2) ram_block_kernel(const BM m, c
   R* part_old = sm.part1;  // upper-segment sums belonging to the step being updated
   R* part_new = sm.part0;
   {
-    R w = 0, acc = 0;
-    ram_walk<R, true>(sm.Lt, pk4, d, row, u_hi, c_hi, j_lo, j_hi, w, acc);
-    ram_walk<R, false>(sm.Lt, pk4, d, row, c_hi, c_lo, j_lo, j_hi, w, acc);
-    ram_walk<R, true>(sm.Lt, pk4, d, row, c_lo, u_lo, j_lo, j_hi, w, acc);
+    const R acc = walk((R)0);
     if (has_row && seg == 1) part_new[row] = acc;
     __syncthreads();
-    if (has_row && seg == 0) sm.v[row] = pk4[4 * row + 2] + acc + part_new[row];
+    if (has_row && seg == 0) sm.v[row] = sm.pn[row] + acc + part_new[row];
     __syncthreads();
   }
   { R* tmp = part_old; part_old = part_new; part_new = tmp; }
@@ -264,9 +258,9 @@ __global__ void __launch_bounds__(kRamThreads, 2) ram_block_kernel(const BM m, c
     if (tid < d) {
       zj = sm.v[tid];
       zsq = zj * zj;
-      pk4[4 * tid] = beta;
-      pk4[4 * tid + 1] = pcur;
-      pk4[4 * tid + 2] = zj * Num<R>::sqrt(Dnew);
+      sm.beta[tid] = beta;
+      sm.pj[tid] = pcur;
+      sm.pn[tid] = zj * Num<R>::sqrt(Dnew);
       sm.Dg[tid] = Dnew;
     }
     pref = block_inclusive_scan<R, NT>(zsq, sm.red);
@@ -274,14 +268,11 @@ __global__ void __launch_bounds__(kRamThreads, 2) ram_block_kernel(const BM m, c
     __syncthreads();
     // ---- the fused pass: update the factor, accumulate the next proposal
     {
-      R w = has_row ? pk4[4 * row + 1] + (seg == 0 ? part_old[row] : (R)0) : (R)0;
-      R acc = 0;
-      ram_walk<R, true>(sm.Lt, pk4, d, row, u_hi, c_hi, j_lo, j_hi, w, acc);
-      ram_walk<R, false>(sm.Lt, pk4, d, row, c_hi, c_lo, j_lo, j_hi, w, acc);
-      ram_walk<R, true>(sm.Lt, pk4, d, row, c_lo, u_lo, j_lo, j_hi, w, acc);
+      const R w0 = has_row ? sm.pj[row] + (seg == 0 ? part_old[row] : (R)0) : (R)0;
+      const R acc = walk(w0);
       if (has_row && seg == 1) part_new[row] = acc;
       __syncthreads();
-      if (has_row && seg == 0) sm.v[row] = pk4[4 * row + 2] + acc + part_new[row];
+      if (has_row && seg == 0) sm.v[row] = sm.pn[row] + acc + part_new[row];
     }
     { R* tmp = part_old; part_old = part_new; part_new = tmp; }
     __syncthreads();
@@ -298,7 +289,7 @@ __global__ void __launch_bounds__(kRamThreads, 2) ram_block_kernel(const BM m, c
   for (int k = tid; k < d; k += NT) {
     st.z[k * C + c] = sm.x[k];
     const R sd = ::sqrt(sm.Dg[k]);
-    sm.y[k] = sd;
+    sm.v[k] = sd;
     st.scale[(int64_t)tri_full(k, k) * C + c] = sd;
   }
   __syncthreads();
@@ -307,7 +298,7 @@ __global__ void __launch_bounds__(kRamThreads, 2) ram_block_kernel(const BM m, c
     while (i * (i - 1) / 2 > e2) --i;
     while ((i + 1) * i / 2 <= e2) ++i;
     const int j = e2 - i * (i - 1) / 2;
-    st.scale[(int64_t)tri_full(i, j) * C + c] = sm.Lt[cm_idx(i, j, d)] * sm.y[j];
+    st.scale[(int64_t)tri_full(i, j) * C + c] = sm.Lt[4 * sm.rb[i] + j] * sm.v[j];
   }
   if (tid == 0) { st.pe[c] = U; st.macc[c] = macc; }
 }

@@ -518,7 +518,7 @@ def run_gaussian_ram(args, world, rank, dev, K, W):
 
     import adaptive_mcmc_b200 as am
 
-    d, Cn, T = 200, 16384, 100  # 16,384 chains PER GPU (weak scaling)
+    d, Cn, T = 200, 16384, 400  # 16,384 chains PER GPU (weak scaling); 400 fused steps per launch
     P = am.models.ar1_precision_chol(d, 0.9)
     s = am.RAM(am.models.gaussian, num_chains=Cn, device=dev, chain_offset=rank * Cn,
                init_strategy=am.init_to_value(torch.zeros(Cn, d)))
@@ -556,9 +556,9 @@ def run_gaussian_ram(args, world, rank, dev, K, W):
         "metric": "chain-steps/sec", "value": rate, "unit": "chain-steps/s", "ms_per_step": ms / K,
         "fused_iterations_per_step": T, "mean_accept_prob": float(b.macc.mean()), "gpu_launches": K,
         "roofline": {"bound": "hbm", "unit": "GB/s", "peak": hbm, "achieved": achieved, "frac": achieved / hbm,
-                     "traffic": _traffic("gaussian_ram_T100"),
+                     "traffic": _traffic(f"gaussian_ram_T{T}"),
                      "note": "algorithmic bytes = 2*4*(d(d+1)/2+2d+3) = 164,024 per chain-step (state round trip, SURVEY 8d); the "
-                             "factor stays in shared memory for the 100 fused steps, so real HBM traffic is ~1/100 of that"},
+                             "factor stays in shared memory for all fused steps of a launch, so real HBM traffic is ~1/400 of that"},
     }
 
 
