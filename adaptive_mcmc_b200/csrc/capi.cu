@@ -212,7 +212,13 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
     case AMCMC_MODEL_STD_NORMAL: rc = run_std_normal(m, st, a, s); break;
     case AMCMC_MODEL_EIGHT_SCHOOLS: rc = run_eight_schools(m, st, a, s); break;
     case AMCMC_MODEL_KIDIQ: rc = run_kidiq(m, st, a, s); break;
-    case AMCMC_MODEL_DIAMONDS: rc = run_diamonds_block(m, st, a, s); break;
+    case AMCMC_MODEL_DIAMONDS: {
+      // many chains, fp32, per-chain adaptation: the likelihood goes to the tensor cores (impl 3 forces, impl 2 forbids)
+      const bool tc = a->adapt && diamonds_tc_available(m) && (a->impl == 3 || (a->impl == 0 && st->n_chains >= 4096));
+      if (a->impl == 3 && !tc) { set_error("amcmc_arwmh_run: tensor-core path unavailable (needs fp32, K = 25, adapt = 1)"); rc = AMCMC_ERR_UNSUPPORTED; break; }
+      rc = tc ? run_diamonds_tc_adapt(m, st, a, s) : run_diamonds_block(m, st, a, s);
+      break;
+    }
     case AMCMC_MODEL_GAUSSIAN: rc = run_gaussian(m, st, a, s); break;
     default:
       set_error("amcmc_arwmh_run: unsupported model %d", m->model_id);

@@ -56,5 +56,7 @@ int potential_gaussian(const amcmc_model* m, int64_t n, const void* q, void* out
 // diamonds: tcgen05 tensor-core path (shared adaptation state) -- diamonds_tc.cu
 int create_diamonds_tc(amcmc_model* m, const double* X, int64_t n, int K, const double* Y);
 void destroy_diamonds_tc(amcmc_model* m);
+bool diamonds_tc_available(const amcmc_model* m);
+int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amcmc_run_args* a, cudaStream_t s);
 
 }  // namespace amcmc

@@ -160,3 +160,95 @@ def test_pooled_adaptation_converges_on_diamonds(diamonds_data):
     b_last = coll["z"]["b"][-20:].double().mean((0, 1)).cpu().numpy()
     ridge = np.linalg.solve(Xc.T @ Xc + sig**2 * np.eye(24), Xc.T @ (Y - Y.mean()))
     assert (np.abs(b_last - ridge) / post_sd).max() < 0.5
+
+
+# ---- diamonds on the tensor cores WITH per-chain adaptation (the full ARWMH.sample) ------------------------
+from oracle import c_oracle as co
+
+
+def _adaptive_sampler(C, q0, impl, **kw):
+    s = am.ARWMH(models.diamonds, num_chains=C, init_strategy=am.init_to_value(torch.from_numpy(q0)), **kw)
+    s.impl = impl
+    return s
+
+
+@pytest.mark.parametrize("C", [256, 1000])
+def test_diamonds_tc_adaptive_matches_oracle(C, diamonds_data):
+    """Shared draws, per-chain adaptation: tensor-core kernel (fp32 state, split-bf16 likelihood) vs the fp64 oracle
+    of the reference step.  Same accept decisions for almost every chain; positions, running mean, factor and step
+    size of those chains agree."""
+    d, T, nw = 26, 40, 10
+    rng = np.random.default_rng(3)
+    q0 = _mode(diamonds_data)[None] + 0.004 * rng.normal(size=(C, d))
+    s = _adaptive_sampler(C, q0, _lib.IMPL_TENSOR)
+    st = s.init(1, num_warmup=nw, init_params=None, model_kwargs=diamonds_data)
+    # a sensible start for the factor: the reference starts from I, which rejects everything on this posterior
+    b = am.ChainBatch.from_state(s.potential, st)
+    b.set_dense_scale(torch.eye(d) * 0.002)
+    st = b.to_state()
+    pot = o.make_potential("diamonds", **diamonds_data)
+    z0 = b.z.t().double().cpu().numpy()
+    ost = o.ARWMHState(0, z0, pot(z0), np.zeros(C), o.ARWMHAdaptState(z0.copy(), np.broadcast_to(np.eye(d) * 0.002, (C, d, d)).copy(),
+                                                                     np.zeros(C)), np.zeros(C), 0)
+    nrm = rng.normal(size=(T, C, d)).astype(np.float32)
+    uni = rng.random(size=(T, C)).astype(np.float32)
+    coll, last = s.run(st, T, draws=(torch.from_numpy(nrm), torch.from_numpy(uni)), record_accept=True)
+    olast, ocoll = co.arwmh_run(ost, "diamonds", T, draws=(nrm.astype(np.float64), uni.astype(np.float64)), record_accept=True,
+                                num_warmup=nw, **diamonds_data)
+    acc_g = coll["accept"].cpu().numpy()
+    same = (acc_g == ocoll["accepts"]).all(axis=0)
+    assert same.mean() > 0.93, same.mean()
+    assert 0.05 < acc_g.mean() < 0.9
+    zg = np.concatenate([v.cpu().numpy().reshape(T, C, -1) for v in coll["z"].values()], axis=-1).astype(np.float64)
+    # fp32 state vs the fp64 oracle: the north star's fp32 bar (1e-3 relative), in practice ~1e-5
+    assert (np.abs(zg[:, same] - ocoll["z"][:, same]) / (1 + np.abs(ocoll["z"][:, same]))).max() < 1e-3
+    a, oa_ = last.adapt_state, olast.adapt_state
+    # The posterior is sharp (sd ~ 0.002 per coordinate) and the step is chaotic in the energies: the ~1e-3 absolute
+    # error of fp32 energies enters lambda through gamma*(alpha - target), lambda scales the next proposal, and the
+    # difference grows ~40x over these 40 steps (scratch/tc_adapt_diag.py prints the growth curve).  So the adapted
+    # state is compared chain by chain: nearly all chains inside the tight band, every chain inside a loose one.
+    def close(x, y, rtol, atol):
+        x = np.asarray(x.cpu().numpy() if hasattr(x, "cpu") else x, np.float64)[same].reshape(int(same.sum()), -1)
+        y = np.asarray(y, np.float64)[same].reshape(int(same.sum()), -1)
+        return (np.abs(x - y) <= atol + rtol * np.abs(y)).all(axis=1)
+
+    def fro(x, y):  # relative Frobenius distance of the factors (elementwise is meaningless for the near-zero entries)
+        x = x.cpu().numpy().astype(np.float64)[same]
+        return np.sqrt(((x - y[same]) ** 2).sum((1, 2)) / (y[same] ** 2).sum((1, 2)))
+
+    checks = {
+        "loc": close(a.loc, oa_.loc, 1e-3, 1e-4),
+        "log_step_size": close(a.log_step_size, oa_.log_step_size, 0, 3e-3),
+        "scale": fro(a.scale, oa_.scale) < 1e-2,
+        "mean_accept_prob": close(last.mean_accept_prob, olast.mean_accept_prob, 0, 3e-3),
+        "as_change": close(last.as_change, olast.as_change, 5e-2, 1e-6),
+        "potential_energy": close(last.potential_energy, olast.potential_energy, 0, 3e-2),
+    }
+    frac = {k: float(v.mean()) for k, v in checks.items()}
+    assert all(f > 0.95 for f in frac.values()), frac
+    assert close(a.log_step_size, oa_.log_step_size, 0, 0.1).all()
+    assert close(a.loc, oa_.loc, 1e-2, 1e-3).all()
+    assert (fro(a.scale, oa_.scale) < 0.2).all()
+    assert int(last.i) == T
+
+
+def test_diamonds_tc_adaptive_matches_block_kernel(diamonds_data):
+    """Philox draws: the tensor-core adaptive path and the exact CUDA-core block kernel run the same chains."""
+    C, d, T = 512, 26, 30
+    rng = np.random.default_rng(8)
+    q0 = _mode(diamonds_data)[None] + 0.004 * rng.normal(size=(C, d))
+    res = {}
+    for impl in (_lib.IMPL_TENSOR, _lib.IMPL_BLOCK):
+        s = _adaptive_sampler(C, q0, impl)
+        st = s.init(2, num_warmup=0, init_params=None, model_kwargs=diamonds_data)
+        b = am.ChainBatch.from_state(s.potential, st)
+        b.set_dense_scale(torch.eye(d) * 0.002)
+        raw = s.run_batch(b, T, thinning=5, record_accept=True)
+        # cut the same stream into two launches (state round trip through the ABI layout)
+        raw2 = s.run_batch(b, 10, collect=())
+        res[impl] = (raw["accept"].cpu().numpy(), b.z.clone(), b.scale.clone(), b.lam.clone(), raw["z"].clone())
+    same = (res[_lib.IMPL_TENSOR][0] == res[_lib.IMPL_BLOCK][0]).all(axis=0)
+    assert same.mean() > 0.9, same.mean()
+    sel = torch.from_numpy(same).to(res[_lib.IMPL_TENSOR][1].device)
+    ref = res[_lib.IMPL_BLOCK][4][:, :, sel]
+    assert ((res[_lib.IMPL_TENSOR][4][:, :, sel] - ref).abs() / (1 + ref.abs())).max() < 1e-3
