@@ -449,6 +449,7 @@ void destroy_diamonds_tc(amcmc_model* m) {
   if (ex->qmean) cudaFree(ex->qmean);
   if (ex->ident) cudaFree(ex->ident);
   if (ex->zero) cudaFree(ex->zero);
+  if (ex->ldl) cudaFree(ex->ldl);
   free(ex);
   m->extra = nullptr;
 }

@@ -44,6 +44,8 @@ struct DiamondsTcExtra {
   float* qmean;      // [26]
   float* ident;      // [351] dummy packed scale for the reference-block kernel
   float* zero;       // [1]
+  float* ldl;        // [ldl_groups][351][128] per-chain LDL^T factors of the adaptive path (see diamonds_tc_adapt.cu)
+  int64_t ldl_groups;
 };
 
 struct TcParams {

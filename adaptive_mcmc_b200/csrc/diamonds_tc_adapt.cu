@@ -4,16 +4,19 @@
 // running mean, LDL^T proposal factor and step size updated between the tensor-core phases.
 //
 // Per-chain adaptation state cannot stay on chip here (128 chains x 1.4 KB per UMMA tile row block, four
-// blocks per SM), so it lives in global memory in the struct-of-arrays layout of the ABI -- the chain index is
-// fastest, so the 128 owner threads of a group touch it with fully coalesced accesses -- and is L2-resident
-// (92 MB at 65,536 chains).  At every step boundary the owner thread of a chain makes ONE software-pipelined pass
-// over its factor, column by column (the next column is loaded before the current one is stored):
+// blocks per SM), so it lives in global memory and is L2-resident (92 MB at 65,536 chains).  The running mean and the
+// positions stay in the struct-of-arrays layout of the ABI (chain index fastest: the 128 owner threads of a group
+// touch them with coalesced accesses).  The proposal factor is re-laid out for the launch: LDL^T form, one block
+// of [351 entries][128 chains] per group, entries in column-major order (TcLdl below).  The strides are then
+// compile-time constants, so every access of the unrolled pass is `base + immediate` and costs no address
+// arithmetic; two small kernels convert from / to the packed Cholesky form of the ABI around the launch.
+// At every step boundary the owner thread of a chain makes ONE pass over its factor:
 //     rank-one update with delta = x_new - loc (Gill-Golub-Murray-Saunders recurrence, as arwmh_small.cuh)
-//     + accumulation of the NEXT proposal  L~'(sqrt(D') .* z_next)  while the column is in registers,
+//     + accumulation of the NEXT proposal  L~'(sqrt(D') .* z_next)  while the entry is in a register,
 // so the factor is read once and written once per step.  The helper warps run one step ahead and only
-// produce the draws (z, u).  During the launch `scale` holds the factor in LDL^T form in place (slot (j,j) = D_j,
-// slot (i,j) = L~_ij); two small kernels convert from / to the Cholesky form of the ABI around the launch.
+// produce the draws (z, u).
 #include <cmath>
+#include <utility>
 #include <vector>
 #include "diamonds_tc.cuh"
 
@@ -22,7 +25,7 @@ namespace amcmc {
 struct TcAdaptParams {
   TcParams p;        // chains, tiles, positions, energies, draws, outputs (as the shared-state kernel)
   float* loc;        // [26][C]
-  float* scale;      // [351][C]  LDL^T form during the launch
+  float* ldl;        // [n_groups][351][128]  LDL^T blocks
   float* lam;        // [C]
   float* asc;        // [C]
   int64_t num_warmup;
@@ -31,26 +34,34 @@ struct TcAdaptParams {
 
 __device__ __forceinline__ int tri_f(int i, int j) { return i * (i + 1) / 2 + j; }
 
-// in-place Cholesky <-> LDL^T of every chain's packed factor
-__global__ void tc_chol_to_ldl_kernel(float* __restrict__ sc, int64_t C) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+constexpr int TC_NE = TC_D * (TC_D + 1) / 2;  // 351 packed entries
+__host__ __device__ constexpr int cm_col(int e) { int j = 0, len = TC_D; while (e >= len) { e -= len; --len; ++j; } return j; }
+__host__ __device__ constexpr int cm_row(int e) { int j = 0, len = TC_D; while (e >= len) { e -= len; --len; ++j; } return j + e; }
+
+// packed Cholesky of the ABI ([351][C], row-major packed) -> LDL^T blocks ([group][351 column-major][128]):
+// slot of (j,j) = D_j = L_jj^2, slot of (i,j) = L~_ij = L_ij / L_jj.  Lanes past C get the identity.
+__global__ void tc_chol_to_ldl_kernel(const float* __restrict__ sc, float* __restrict__ ldl, int64_t C) {
+  const int64_t c = (int64_t)blockIdx.x * TC_M + threadIdx.x;
+  float* blk = ldl + (int64_t)blockIdx.x * TC_NE * TC_M + threadIdx.x;
+  int e = 0;
 #pragma unroll 1
   for (int j = 0; j < TC_D; ++j) {
-    const float dg = sc[(int64_t)tri_f(j, j) * C + c];
+    const float dg = c < C ? sc[(int64_t)tri_f(j, j) * C + c] : 1.f;
     const float inv = 1.0f / dg;
-    for (int i = j + 1; i < TC_D; ++i) sc[(int64_t)tri_f(i, j) * C + c] *= inv;
-    sc[(int64_t)tri_f(j, j) * C + c] = dg * dg;
+    blk[(e++) * TC_M] = dg * dg;
+    for (int i = j + 1; i < TC_D; ++i) blk[(e++) * TC_M] = c < C ? sc[(int64_t)tri_f(i, j) * C + c] * inv : 0.f;
   }
 }
-__global__ void tc_ldl_to_chol_kernel(float* __restrict__ sc, int64_t C) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void tc_ldl_to_chol_kernel(const float* __restrict__ ldl, float* __restrict__ sc, int64_t C) {
+  const int64_t c = (int64_t)blockIdx.x * TC_M + threadIdx.x;
   if (c >= C) return;
+  const float* blk = ldl + (int64_t)blockIdx.x * TC_NE * TC_M + threadIdx.x;
+  int e = 0;
 #pragma unroll 1
   for (int j = 0; j < TC_D; ++j) {
-    const float sd = sqrtf(sc[(int64_t)tri_f(j, j) * C + c]);
-    for (int i = j + 1; i < TC_D; ++i) sc[(int64_t)tri_f(i, j) * C + c] *= sd;
+    const float sd = sqrtf(blk[(e++) * TC_M]);
     sc[(int64_t)tri_f(j, j) * C + c] = sd;
+    for (int i = j + 1; i < TC_D; ++i) sc[(int64_t)tri_f(i, j) * C + c] = blk[(e++) * TC_M] * sd;
   }
 }
 
@@ -73,94 +84,118 @@ __global__ void tc_mean_finish_kernel(const double* __restrict__ acc, int64_t C,
 }
 
 // One pass over the chain's LDL^T factor in global memory (see the file header).
-//   UPDATE : apply (1-gamma) L D L^T + gamma w w^T   (w is consumed);  otherwise the factor is only read
+//   upd    : apply (1-gamma) L D L^T + gamma w w^T (w is consumed).  Without it the caller passes gamma = 0 and
+//            w = 0, which makes every expression below reproduce the old factor bit for bit, and nothing is stored.
 //   WANT   : accumulate |L' e^lam' - L e^lam|_F^2  (arwmh.py:197)
 //   acc_i  = sum_{j<=i} L~'_ij sqrt(D'_j) zn_j     (zn: next draws in shared memory, stride TC_M; zero if !have_next)
-template <bool UPDATE, bool WANT>
-__device__ __forceinline__ float tc_column_pass(float* __restrict__ sc, int64_t C, int64_t c, const float* zn, bool have_next,
-                                                float (&w)[TC_D], float gamma, float el_old, float el_new,
-                                                float (&acc)[TC_D]) {
-  float t = 1.f, ss = 0.f;
-  const float omg = 1.f - gamma;
-#pragma unroll
-  for (int k = 0; k < TC_D; ++k) acc[k] = 0.f;
-  float nxt[TC_D];  // prefetched column: nxt[j] = D_j, nxt[i > j] = L~_ij
-#pragma unroll
-  for (int i = 0; i < TC_D; ++i) nxt[i] = sc[(int64_t)tri_f(i, 0) * C + c];
-#pragma unroll
-  for (int j = 0; j < TC_D; ++j) {
-    float cur[TC_D];
-#pragma unroll
-    for (int i = j; i < TC_D; ++i) cur[i] = nxt[i];
-    if (j + 1 < TC_D) {
-#pragma unroll
-      for (int i = j + 1; i < TC_D; ++i) nxt[i] = sc[(int64_t)tri_f(i, j + 1) * C + c];  // in flight during column j
-    }
-    const float Dold = cur[j];
-    float Dnew = Dold, coef = 0.f, wj = 0.f;
-    if (UPDATE) {
-      const bool pos = Dold > 0.f;  // a non-positive pivot leaves its column untouched
-      const float Dj = omg * Dold;
-      wj = w[j];
-      const float cw = gamma * wj;
-      const float g = fmaf(cw * wj, t, Dj);
-      const float tr = __fdividef(t, g);
-      if (pos) { coef = cw * tr; t = Dj * tr; Dnew = g; } else { wj = 0.f; }
-      sc[(int64_t)tri_f(j, j) * C + c] = Dnew;
-    }
+// The 351 entries are visited column by column through a ring of TC_RING registers: entry e + TC_RING is requested
+// when entry e is consumed, so TC_RING loads stay in flight per thread for the whole pass (the pass is bound by L2
+// latency, not by bandwidth or issue).  The visit is unrolled at compile time (fold over an index sequence) so the
+// ring, w and acc are registers; a rolled loop would put them in local memory, which misses the ~30 KB of L1 left
+// beside the tiles.
+constexpr int TC_RING = 64;
+
+template <bool WANT>
+struct PassCtx {
+  float* col;      // this chain's lane of its group block: entry e at col[e * TC_M]
+  const float* zn;
+  bool have_next, upd;
+  float gamma, omg, el_old, el_new;
+  float t, ss, wj, coef, yj, so, sn;
+  float ring[TC_RING];
+  float w[TC_D], acc[TC_D];
+};
+
+template <bool WANT, int E>
+__device__ __forceinline__ void tc_pass_entry(PassCtx<WANT>& x) {
+  constexpr int j = cm_col(E), i = cm_row(E);
+  const float v = x.ring[E % TC_RING];
+  if constexpr (E + TC_RING < TC_NE) x.ring[E % TC_RING] = x.col[(E + TC_RING) * TC_M];
+  if constexpr (i == j) {
+    const float Dold = v;
+    const bool pos = Dold > 0.f;  // a non-positive pivot leaves its column untouched
+    const float Dj = x.omg * Dold;
+    const float wj = x.w[j];
+    const float cw = x.gamma * wj;
+    const float g = fmaf(cw * wj, x.t, Dj);
+    const float tr = __fdividef(x.t, g);
+    const float Dnew = pos ? g : Dold;
+    x.coef = pos ? cw * tr : 0.f;
+    x.t = pos ? Dj * tr : x.t;
+    x.wj = pos ? wj : 0.f;
+    if (x.upd) x.col[E * TC_M] = Dnew;
     const float sn_raw = sqrtf(Dnew);
-    const float yj = have_next ? sn_raw * zn[j * TC_M] : 0.f;
-    acc[j] += yj;
-    float so = 0.f, sn = 0.f;
+    x.yj = x.have_next ? sn_raw * x.zn[j * TC_M] : 0.f;
+    x.acc[j] += x.yj;
     if (WANT) {
-      so = sqrtf(Dold) * el_old;
-      sn = sn_raw * el_new;
-      const float dd = sn - so;
-      ss = fmaf(dd, dd, ss);
+      x.so = sqrtf(Dold) * x.el_old;
+      x.sn = sn_raw * x.el_new;
+      const float dd = x.sn - x.so;
+      x.ss = fmaf(dd, dd, x.ss);
     }
-#pragma unroll
-    for (int i = j + 1; i < TC_D; ++i) {
-      const float Lo = cur[i];
-      float Ln = Lo;
-      if (UPDATE) {
-        w[i] = fmaf(-wj, Lo, w[i]);
-        Ln = fmaf(coef, w[i], Lo);
-        sc[(int64_t)tri_f(i, j) * C + c] = Ln;
-      }
-      acc[i] = fmaf(Ln, yj, acc[i]);
-      if (WANT) {
-        const float df = fmaf(Ln, sn, -(Lo * so));
-        ss = fmaf(df, df, ss);
-      }
+  } else {
+    const float Lo = v;
+    x.w[i] = fmaf(-x.wj, Lo, x.w[i]);
+    const float Ln = fmaf(x.coef, x.w[i], Lo);
+    if (x.upd) x.col[E * TC_M] = Ln;
+    x.acc[i] = fmaf(Ln, x.yj, x.acc[i]);
+    if (WANT) {
+      const float df = fmaf(Ln, x.sn, -(Lo * x.so));
+      x.ss = fmaf(df, df, x.ss);
     }
   }
-  return ss;
+}
+template <bool WANT, size_t... E>
+__device__ __forceinline__ void tc_pass_all(PassCtx<WANT>& x, std::index_sequence<E...>) {
+  (tc_pass_entry<WANT, (int)E>(x), ...);
+}
+template <bool WANT, size_t... E>
+__device__ __forceinline__ void tc_pass_fill(PassCtx<WANT>& x, std::index_sequence<E...>) {
+  ((x.ring[E] = x.col[(int)E * TC_M]), ...);
+}
+
+template <bool WANT>
+__device__ __forceinline__ float tc_column_pass(float* __restrict__ col, const float* zn, bool have_next,
+                                                bool upd, float (&w)[TC_D], float gamma, float el_old, float el_new,
+                                                float (&acc)[TC_D]) {
+  PassCtx<WANT> x;
+  x.col = col; x.zn = zn; x.have_next = have_next; x.upd = upd;
+  x.gamma = gamma; x.omg = 1.f - gamma; x.el_old = el_old; x.el_new = el_new;
+  x.t = 1.f; x.ss = 0.f; x.wj = 0.f; x.coef = 0.f; x.yj = 0.f; x.so = 0.f; x.sn = 0.f;
+  tc_pass_fill<WANT>(x, std::make_index_sequence<TC_RING>{});
+#pragma unroll
+  for (int k = 0; k < TC_D; ++k) { x.w[k] = w[k]; x.acc[k] = 0.f; }
+  tc_pass_all<WANT>(x, std::make_index_sequence<TC_NE>{});
+#pragma unroll
+  for (int k = 0; k < TC_D; ++k) acc[k] = x.acc[k];
+  return x.ss;
 }
 
 // proposal -> A' row (split bf16), scalar part of U', shadow position buffer.  Returns via references.
 __device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const float* sRef, unsigned char* sA, int g, int row,
                                                  uint64_t* a_ready_g, double n_rows, double cst, double& Up_part, double& inv2var) {
   float dq = 0.f;
-  uint16_t ak[TC_KP];
+  uint32_t hi[TC_KC], lo[TC_KC];  // bf16 bit patterns in the low halves
 #pragma unroll
   for (int k = 0; k < TC_KC; ++k) {
     const float dlt = xp[k] - sRef[REF_Q + k];
     dq = fmaf(dlt, sRef[REF_G2 + k], dq);
-    const uint16_t hi = f2bf(dlt);
-    ak[k] = hi;
-    ak[TC_KC + k] = f2bf(dlt - bf2f(hi));
-    ak[2 * TC_KC + k] = hi;
+    const uint16_t h = f2bf(dlt);
+    hi[k] = h;
+    lo[k] = f2bf(dlt - bf2f(h));
   }
-#pragma unroll
-  for (int k = 3 * TC_KC; k < TC_KP; ++k) ak[k] = 0;
+  // K' layout: [hi(25) | lo(25) | hi(25) | 0(5)]
+  auto elem = [&](int k) -> uint32_t {
+    return k < TC_KC ? hi[k] : (k < 2 * TC_KC ? lo[k - TC_KC] : (k < 3 * TC_KC ? hi[k - 2 * TC_KC] : 0u));
+  };
   unsigned char* arow = sA + g * TC_A_BYTES + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
   for (int kc = 0; kc < TC_KP / 8; ++kc) {
     uint4 v;
-    v.x = (uint32_t)ak[8 * kc] | ((uint32_t)ak[8 * kc + 1] << 16);
-    v.y = (uint32_t)ak[8 * kc + 2] | ((uint32_t)ak[8 * kc + 3] << 16);
-    v.z = (uint32_t)ak[8 * kc + 4] | ((uint32_t)ak[8 * kc + 5] << 16);
-    v.w = (uint32_t)ak[8 * kc + 6] | ((uint32_t)ak[8 * kc + 7] << 16);
+    v.x = elem(8 * kc) | (elem(8 * kc + 1) << 16);
+    v.y = elem(8 * kc + 2) | (elem(8 * kc + 3) << 16);
+    v.z = elem(8 * kc + 4) | (elem(8 * kc + 5) << 16);
+    v.w = elem(8 * kc + 6) | (elem(8 * kc + 7) << 16);
     *reinterpret_cast<uint4*>(arow + kc * (TC_M / 8) * 128) = v;
   }
   fence_proxy_async_smem();
@@ -174,6 +209,21 @@ __device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const 
   Up_part = (double)(0.5f * sb + 2.f * log1pf(ti * ti * (1.f / 3.f)) + 2.f * log1pf(ts * ts * (1.f / 3.f))) +
             (n_rows - 1.0) * (double)s + cst + inv2var * (*reinterpret_cast<const double*>(sRef + REF_RSS) - (double)dq);
 }
+
+// Warp roles: warps 0-7 = the two sampler warpgroups (TMEM epilogue + per-chain state), warp 8 = TMA producer,
+// warp 9 = MMA issuer, warps 10-11 = draws.  The sampler warpgroups take the registers the third one gives up
+// (setmaxnreg: 2 x 128 x 208 + 128 x 88 = 384 x 168, the CTA's pool at launch), which is what keeps the unrolled column pass spill-free.
+constexpr int kTmaWarp = TC_EPI_WARPS, kMmaWarp = TC_EPI_WARPS + 1;
+constexpr int kSamplerRegs = 208, kServiceRegs = 88, kLaunchRegs = 168;  // launch: 65536 / 384 rounded down to 8
+static_assert(TC_EPI_WARPS == 8 && TC_HELP_WARPS == 2, "warp roles assume 8 sampler + 4 service warps");
+static_assert(32 * TC_EPI_WARPS * kSamplerRegs + 128 * kServiceRegs <= TC_THREADS * kLaunchRegs, "the pool is what the CTA got at launch");
+
+#ifdef AMCMC_TC_TIMING
+__device__ unsigned long long tc_dbg[16];
+#define TC_T(k) do { if (dbg) { const long long now_ = clock64(); tc_dbg[k] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
+#else
+#define TC_T(k) do { } while (0)
+#endif
 
 template <bool EXTERNAL>
 __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const TcAdaptParams ap) {
@@ -194,7 +244,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
   float* sExch = reinterpret_cast<float*>(smem + TcSmem::OFF_EXCH);
   float* sV = reinterpret_cast<float*>(smem + TcSmem::OFF_V);  // [TC_GR][27][TC_M]: next draws z[26], u
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the role branches are warp-uniform
   const int per = p.n_groups / (int)gridDim.x, rem = p.n_groups % (int)gridDim.x;
   const int g_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
   const int g_count = per + ((int)blockIdx.x < rem ? 1 : 0);
@@ -213,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   for (int e = tid; e < REF_FLOATS; e += TC_THREADS) sRef[e] = p.ref[e];
   tc_fence_before();
   __syncthreads();
@@ -223,11 +274,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
   const int n_rounds = (g_count + TC_GR - 1) / TC_GR;
   uint32_t x_it = 0, acc_it = 0, a_it = 0;
 
-  for (int rnd = 0; rnd < n_rounds; ++rnd) {
-    const int G = min(TC_GR, g_count - rnd * TC_GR);
-    const int g0 = g_begin + rnd * TC_GR;
+#define TC_ROUND_BEGIN                                   \
+  for (int rnd = 0; rnd < n_rounds; ++rnd) {             \
+    const int G = min(TC_GR, g_count - rnd * TC_GR);     \
+    const int g0 = g_begin + rnd * TC_GR;                \
+    (void)g0;
+#define TC_ROUND_END                                     \
+    a_it += (uint32_t)p.n_steps;                         \
+  }
+#define TC_SERVICE_REGS asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs))
 
-    if (warp == 0) {
+  {
+    if (warp >= TC_EPI_WARPS) TC_SERVICE_REGS;  // one instruction for the whole service warpgroup (.aligned)
+    if (warp == kTmaWarp) {
+      TC_ROUND_BEGIN
       if (lane == 0) {  // ===== TMA producer =====
         for (int64_t st = 0; st < p.n_steps; ++st)
           for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
@@ -237,7 +297,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
             tma_load_1d(sX + s * TC_TILE_BYTES, p.Xcanon + (size_t)tile * (TC_TILE_BYTES / 2), TC_TILE_BYTES, &x_full[s]);
           }
       }
-    } else if (warp == 1) {
+      TC_ROUND_END
+    } else if (warp == kMmaWarp) {
+      TC_ROUND_BEGIN
       if (lane == 0) {  // ===== MMA issuer =====
         const uint32_t idesc = make_idesc_bf16_f32(TC_M, TC_TILE_N);
         constexpr uint32_t a_kstride = (TC_M / 8) * 128, b_kstride = (TC_TILE_N / 8) * 128;
@@ -263,9 +325,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
           }
         }
       }
-    } else if (warp >= 2 + TC_EPI_WARPS) {
+      TC_ROUND_END
+    } else if (warp > kMmaWarp) {
+      TC_ROUND_BEGIN
       // ===== helper warps: the draws of every chain, one step ahead (arwmh.py:162-165,174) =====
-      const int ht = tid - 32 * (2 + TC_EPI_WARPS);
+      const int ht = tid - 32 * (kMmaWarp + 1);
       for (int64_t st = 0; st < p.n_steps; ++st) {
         const int64_t it = p.i0 + st;
         for (int g = 0; g < G; ++g) {
@@ -290,174 +354,212 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
           mbar_arrive(&v_full[g]);
         }
       }
+      TC_ROUND_END
     } else {
       // ===== epilogue / sampler threads =====
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSamplerRegs));
+      TC_ROUND_BEGIN
       const int q4 = warp & 3;
-      const int half = (warp - 2) >> 2;
+      const int half = warp >> 2;
       const int row = q4 * 32 + lane;
       const uint32_t t_lane = ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 128);
-      float Ucur[2] = {0.f, 0.f}, macc[2] = {0.f, 0.f}, lam[2] = {0.f, 0.f}, uacc[2] = {2.f, 2.f};
-      double Up_part[2] = {0.0, 0.0}, inv2var[2] = {0.0, 0.0};
-      int cur[2] = {0, 0};
+      // The two chains a thread owns (groups 2*half and 2*half+1) are served by ONE copy of the code: the loop
+      // over them is rolled and the per-chain scalars are swapped at its end, so they stay in registers.
+      float UcurA = 0.f, UcurB = 0.f, maccA = 0.f, maccB = 0.f, lamA = 0.f, lamB = 0.f, uaccA = 2.f, uaccB = 2.f;
+      double UppA = 0.0, UppB = 0.0, i2vA = 0.0, i2vB = 0.0;
+      int curA = 0, curB = 0;
       int64_t until_collect = p.collect_start + p.thinning;
       int64_t sidx = 0;
-
-      // builds the proposal of step `st_next` for owned slot o from the current position, writes A', energy parts
-      auto propose = [&](int o, int g, int64_t c, bool live, int64_t cc, const float (&acc)[TC_D], float el, uint32_t vphase) {
-        const float* xsrc = cur[o] ? p.xprop : p.z;
-        float* xdst = cur[o] ? p.z : p.xprop;
-        const float* vrow = sV + (size_t)g * 27 * TC_M + row;
-        float xp[TC_D];
-#pragma unroll
-        for (int i = 0; i < TC_D; ++i) {
-          xp[i] = xsrc[(int64_t)i * p.C + cc] + fmaf(el, acc[i], ap.eps * vrow[i * TC_M]);  // arwmh.py:166-167
-          if (live) xdst[(int64_t)i * p.C + c] = xp[i];
-        }
-        uacc[o] = vrow[26 * TC_M];
-        mbar_arrive(&v_empty[g]);
-        tc_emit_proposal(xp, sRef, sA, g, row, &a_ready[g], (double)p.n_rows, p.cst, Up_part[o], inv2var[o]);
-        (void)vphase;
-      };
-
-      // ---- prologue: state of the owned chains, proposal of the first step (no update yet)
-#pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        const int g = 2 * half + o;
+#pragma unroll 1
+      for (int rep = 0; rep < 2; ++rep) {
+        const int g = 2 * half + rep;
         if (g < G) {
           const int64_t c = (int64_t)(g0 + g) * TC_M + row;
-          const bool live = c < p.C;
-          const int64_t cc = live ? c : (p.C - 1);
-          Ucur[o] = p.pe[cc]; macc[o] = p.macc[cc]; lam[o] = ap.lam[cc];
-          mbar_wait(&v_full[g], a_it & 1);
-          float w[TC_D], acc[TC_D];
-#pragma unroll
-          for (int k = 0; k < TC_D; ++k) w[k] = 0.f;
-          tc_column_pass<false, false>(ap.scale, p.C, cc, sV + (size_t)g * 27 * TC_M + row, true, w, 0.f, 1.f, 1.f, acc);
-          propose(o, g, c, live, cc, acc, __expf(lam[o]), 0);
+          const int64_t cc = c < p.C ? c : (p.C - 1);
+          UcurA = p.pe[cc]; maccA = p.macc[cc]; lamA = ap.lam[cc];
         }
+        { float tf; tf = UcurA; UcurA = UcurB; UcurB = tf; tf = maccA; maccA = maccB; maccB = tf; tf = lamA; lamA = lamB; lamB = tf; }
       }
 
-      for (int64_t st = 0; st < p.n_steps; ++st) {
+#ifdef AMCMC_TC_TIMING
+      const bool dbg = (blockIdx.x == 0 && tid == 0);
+      long long tlast = clock64();
+#endif
+      // st = -1 builds the proposal of the first step (no accept, no update)
+      for (int64_t st = -1; st < p.n_steps; ++st) {
+        TC_T(0);
         const int64_t it = p.i0 + st;
-        float rss[TC_GR];
+        float mine0 = 0.f, mine1 = 0.f;
+        if (st >= 0) {
+          float rss[TC_GR];
 #pragma unroll
-        for (int g = 0; g < TC_GR; ++g) rss[g] = 0.f;
-        // ---- likelihood: sum_n m_n^2 from the TMEM accumulators
-        for (int tile = 0; tile < p.n_tiles; ++tile) {
+          for (int g = 0; g < TC_GR; ++g) rss[g] = 0.f;
+          // ---- likelihood: sum_n m_n^2 from the TMEM accumulators
+          for (int tile = 0; tile < p.n_tiles; ++tile) {
 #pragma unroll
-          for (int g = 0; g < TC_GR; ++g) {
-            if (g < G) {
-              const int b = acc_it & 1;
-              mbar_wait(&acc_full[b], (acc_it >> 1) & 1);
-              tc_fence_after();
-              const float ss = epilogue_sumsq_half(tmem_base + t_lane + (uint32_t)(b * TC_TILE_N));
-              tc_fence_before();
-              mbar_arrive(&acc_empty[b]);
-              rss[g] += ss;
-              ++acc_it;
+            for (int g = 0; g < TC_GR; ++g) {
+              if (g < G) {
+                const int b = acc_it & 1;
+                mbar_wait(&acc_full[b], (acc_it >> 1) & 1);
+                tc_fence_after();
+                const float ss = epilogue_sumsq_half(tmem_base + t_lane + (uint32_t)(b * TC_TILE_N));
+                tc_fence_before();
+                mbar_arrive(&acc_empty[b]);
+                rss[g] += ss;
+                ++acc_it;
+              }
             }
           }
-        }
 #pragma unroll
-        for (int g = 0; g < TC_GR; ++g)
-          if (g < G && (g >> 1) != half) sExch[g * TC_M + row] = rss[g];
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-        float mine[2];
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          const int g = 2 * half + o;
-          mine[o] = (g < G) ? rss[g] + sExch[g * TC_M + row] : 0.f;
+          for (int g = 0; g < TC_GR; ++g)
+            if (g < G && (g >> 1) != half) sExch[g * TC_M + row] = rss[g];
+          TC_T(1);
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+          const float own0 = half ? rss[2] : rss[0], own1 = half ? rss[3] : rss[1];
+          if (2 * half < G) mine0 = own0 + sExch[(2 * half) * TC_M + row];
+          if (2 * half + 1 < G) mine1 = own1 + sExch[(2 * half + 1) * TC_M + row];
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+          TC_T(2);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-
-        const bool collect_now = (--until_collect == 0);
-        if (collect_now) until_collect = p.thinning;
+        bool collect_now = false;
+        if (st >= 0) {
+          collect_now = (--until_collect == 0);
+          if (collect_now) until_collect = p.thinning;
+        }
         const bool last = (st == p.n_steps - 1);
         const int64_t n = (it < ap.num_warmup) ? (it + 1) : (it + 1 - ap.num_warmup);
         const float nf = (float)n;
-        const float gamma = (n == 1) ? 1.f : Num<float>::pow_neg(nf, ap.lr_decay);
-#pragma unroll
-        for (int o = 0; o < 2; ++o) {
-          const int g = 2 * half + o;
+        const float gamma_n = (n == 1) ? 1.f : Num<float>::pow_neg(nf, ap.lr_decay);
+#pragma unroll 1
+        for (int rep = 0; rep < 2; ++rep) {
+          const int g = 2 * half + rep;
           if (g < G) {
             const int64_t c = (int64_t)(g0 + g) * TC_M + row;
             const bool live = c < p.C;
             const int64_t cc = live ? c : (p.C - 1);
-            // ---- accept / reject (arwmh.py:170-178)
-            float Up = (float)(Up_part[o] + inv2var[o] * (double)mine[o]);
-            if (Up != Up) Up = INFINITY;
-            const float e = __expf(Ucur[o] - Up);
-            const float alpha = (e > 1.f) ? 1.f : e;
-            const bool accd = uacc[o] < alpha;
-            macc[o] = fmaf(alpha - macc[o], Num<float>::rcp(nf), macc[o]);  // :185
-            if (accd) { cur[o] ^= 1; Ucur[o] = Up; }
-            const float* xs = cur[o] ? p.xprop : p.z;
-            if (live) {
-              if (p.out_acc) p.out_acc[st * p.C + c] = (uint8_t)accd;
-              if (collect_now) {
-                if (p.out_z) {
-#pragma unroll
-                  for (int k = 0; k < TC_D; ++k) p.out_z[(sidx * TC_D + k) * p.C + c] = xs[(int64_t)k * p.C + c];
-                }
-                if (p.out_pe) p.out_pe[sidx * p.C + c] = Ucur[o];
-              }
-            }
-            // ---- adaptation (:188-193): mean, step size, rank-one factor update fused with the next proposal
             float w[TC_D], acc[TC_D];
-            float dabs = 0.f;
+            float gamma = 0.f, el_old = 1.f, el_new;
+            bool upd = false;
+            if (st >= 0) {
+              // ---- accept / reject (arwmh.py:170-178)
+              const float mine = rep ? mine1 : mine0;
+              float Up = (float)(UppA + i2vA * (double)mine);
+              if (Up != Up) Up = INFINITY;
+              const float e = __expf(UcurA - Up);
+              const float alpha = (e > 1.f) ? 1.f : e;
+              const bool accd = uaccA < alpha;
+              maccA = fmaf(alpha - maccA, Num<float>::rcp(nf), maccA);  // :185
+              if (accd) { curA ^= 1; UcurA = Up; }
+              const float* xs = curA ? p.xprop : p.z;
+              if (live) {
+                if (p.out_acc) p.out_acc[st * p.C + c] = (uint8_t)accd;
+                if (collect_now) {
+                  if (p.out_z) {
 #pragma unroll
-            for (int k = 0; k < TC_D; ++k) {
-              const float mu = ap.loc[(int64_t)k * p.C + cc];
-              const float dl = xs[(int64_t)k * p.C + cc] - mu;
-              if (live) ap.loc[(int64_t)k * p.C + c] = fmaf(gamma, dl, mu);
-              w[k] = dl;
-              dabs += fabsf(dl);
+                    for (int k = 0; k < TC_D; ++k) p.out_z[(sidx * TC_D + k) * p.C + c] = xs[(int64_t)k * p.C + c];
+                  }
+                  if (p.out_pe) p.out_pe[sidx * p.C + c] = UcurA;
+                }
+              }
+              // ---- adaptation (:188-193): mean, step size, rank-one factor update fused with the next proposal
+              float dabs = 0.f;
+              float mu[TC_D];
+#pragma unroll
+              for (int k = 0; k < TC_D; ++k) {  // all loads first: the stores below may alias them for the compiler
+                mu[k] = ap.loc[(int64_t)k * p.C + cc];
+                w[k] = xs[(int64_t)k * p.C + cc];
+              }
+#pragma unroll
+              for (int k = 0; k < TC_D; ++k) {
+                w[k] -= mu[k];
+                if (live) ap.loc[(int64_t)k * p.C + c] = fmaf(gamma_n, w[k], mu[k]);
+                dabs += fabsf(w[k]);
+              }
+              upd = live && (n != 1) && (dabs < Num<float>::kBig);  // padding lanes must never write a factor
+              el_old = __expf(lamA);
+              lamA = fmaf(gamma_n, alpha - ap.target, lamA);
+              el_new = __expf(lamA);
+            } else {
+              el_new = __expf(lamA);
             }
-            const bool ok = live && (n != 1) && (dabs < Num<float>::kBig);  // padding lanes must never write a factor
-            const float el_old = __expf(lam[o]);
-            const float lam_new = fmaf(gamma, alpha - ap.target, lam[o]);
-            const float el_new = __expf(lam_new);
-            lam[o] = lam_new;
-            const bool have_next = !last;
-            if (have_next) mbar_wait(&v_full[g], (a_it + (uint32_t)st + 1u) & 1);
+            if (upd) {
+              gamma = gamma_n;
+            } else {
+#pragma unroll
+              for (int k = 0; k < TC_D; ++k) w[k] = 0.f;
+            }
             const float* zn = sV + (size_t)g * 27 * TC_M + row;
-            float ss = 0.f;
+            float* fcol = ap.ldl + (int64_t)(g0 + g) * (TC_NE * TC_M) + row;
+            TC_T(3);
             if (last) {
-              ss = ok ? tc_column_pass<true, true>(ap.scale, p.C, cc, zn, false, w, gamma, el_old, el_new, acc)
-                      : tc_column_pass<false, true>(ap.scale, p.C, cc, zn, false, w, gamma, el_old, el_new, acc);
+              const float ss = tc_column_pass<true>(fcol, zn, false, upd, w, gamma, el_old, el_new, acc);
               if (live) ap.asc[c] = sqrtf(ss);  // :197
             } else {
-              if (ok) tc_column_pass<true, false>(ap.scale, p.C, cc, zn, true, w, gamma, el_old, el_new, acc);
-              else tc_column_pass<false, false>(ap.scale, p.C, cc, zn, true, w, gamma, el_old, el_new, acc);
-              propose(o, g, c, live, cc, acc, el_new, 0);
+              mbar_wait(&v_full[g], (a_it + (uint32_t)(st + 1)) & 1);
+              TC_T(4);
+              tc_column_pass<false>(fcol, zn, true, upd, w, gamma, el_old, el_new, acc);
+              TC_T(5);
+              // ---- proposal of step st+1 from the current position (arwmh.py:166-167), A' row, energy parts
+              const float* xsrc = curA ? p.xprop : p.z;
+              float* xdst = curA ? p.z : p.xprop;
+              float xp[TC_D];
+#pragma unroll
+              for (int i = 0; i < TC_D; ++i) xp[i] = xsrc[(int64_t)i * p.C + cc];
+#pragma unroll
+              for (int i = 0; i < TC_D; ++i) {
+                xp[i] += fmaf(el_new, acc[i], ap.eps * zn[i * TC_M]);
+                if (live) xdst[(int64_t)i * p.C + c] = xp[i];
+              }
+              uaccA = zn[26 * TC_M];
+              mbar_arrive(&v_empty[g]);
+              tc_emit_proposal(xp, sRef, sA, g, row, &a_ready[g], (double)p.n_rows, p.cst, UppA, i2vA);
+              TC_T(6);
             }
+          }
+          {  // swap the two owned chains
+            float tf; double td; int ti;
+            tf = UcurA; UcurA = UcurB; UcurB = tf;
+            tf = maccA; maccA = maccB; maccB = tf;
+            tf = lamA; lamA = lamB; lamB = tf;
+            tf = uaccA; uaccA = uaccB; uaccB = tf;
+            td = UppA; UppA = UppB; UppB = td;
+            td = i2vA; i2vA = i2vB; i2vB = td;
+            ti = curA; curA = curB; curB = ti;
           }
         }
         if (collect_now) ++sidx;
       }
       // ---- write back the per-chain scalars and the position if it ended in the shadow buffer
-#pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        const int g = 2 * half + o;
+#pragma unroll 1
+      for (int rep = 0; rep < 2; ++rep) {
+        const int g = 2 * half + rep;
         if (g < G) {
           const int64_t c = (int64_t)(g0 + g) * TC_M + row;
           if (c < p.C) {
-            p.pe[c] = Ucur[o];
-            p.macc[c] = macc[o];
-            ap.lam[c] = lam[o];
-            if (cur[o]) {
+            p.pe[c] = UcurA;
+            p.macc[c] = maccA;
+            ap.lam[c] = lamA;
+            if (curA) {
 #pragma unroll
               for (int k = 0; k < TC_D; ++k) p.z[(int64_t)k * p.C + c] = p.xprop[(int64_t)k * p.C + c];
             }
           }
         }
+        float tf; int ti;
+        tf = UcurA; UcurA = UcurB; UcurB = tf;
+        tf = maccA; maccA = maccB; maccB = tf;
+        tf = lamA; lamA = lamB; lamB = tf;
+        ti = curA; curA = curB; curB = ti;
       }
+      TC_ROUND_END
     }
-    a_it += (uint32_t)p.n_steps;
   }
+#undef TC_ROUND_BEGIN
+#undef TC_ROUND_END
+#undef TC_SERVICE_REGS
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 // from diamonds_tc.cu
@@ -472,7 +574,6 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
   int rc = diamonds_tc_prepare(m, st->n_chains, &ap.p, st, a);
   if (rc) return rc;
   ap.loc = (float*)st->loc;
-  ap.scale = (float*)st->scale;
   ap.lam = (float*)st->log_step_size;
   ap.asc = (float*)st->as_change;
   ap.num_warmup = a->num_warmup;
@@ -485,8 +586,15 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
   tc_mean_kernel<<<dim3(64, TC_D), 256, 0, s>>>((const float*)st->z, C, ex->mean_acc);
   tc_mean_finish_kernel<<<1, 128, 0, s>>>(ex->mean_acc, C, ex->qmean, ex->ident, ex->zero);
   diamonds_tc_launch_ref(m, ex->qmean, ex->ident, ex->zero, 0.0, s);
-  const unsigned gridc = (unsigned)((C + 127) / 128);
-  tc_chol_to_ldl_kernel<<<gridc, 128, 0, s>>>(ap.scale, C);
+  if (ex->ldl_groups < ap.p.n_groups) {
+    if (ex->ldl) cudaFree(ex->ldl);
+    ex->ldl = nullptr;
+    ex->ldl_groups = 0;
+    if ((rc = check_cuda(cudaMalloc(&ex->ldl, (size_t)ap.p.n_groups * TC_NE * TC_M * sizeof(float)), "cudaMalloc(ldl)"))) return rc;
+    ex->ldl_groups = ap.p.n_groups;
+  }
+  ap.ldl = ex->ldl;
+  tc_chol_to_ldl_kernel<<<ap.p.n_groups, TC_M, 0, s>>>((const float*)st->scale, ap.ldl, C);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -499,8 +607,15 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     diamonds_tc_adapt_kernel<false><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
   }
   if ((rc = check_cuda(cudaGetLastError(), "diamonds_tc_adapt_kernel launch"))) return rc;
-  tc_ldl_to_chol_kernel<<<gridc, 128, 0, s>>>(ap.scale, C);
+  tc_ldl_to_chol_kernel<<<ap.p.n_groups, TC_M, 0, s>>>(ap.ldl, (float*)st->scale, C);
   return check_cuda(cudaGetLastError(), "tc_ldl_to_chol_kernel launch");
 }
 
 }  // namespace amcmc
+
+#ifdef AMCMC_TC_TIMING
+extern "C" void amcmc_debug_tc_timing(unsigned long long* out, int reset) {
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(amcmc::tc_dbg, z, sizeof(z)); }
+  else cudaMemcpyFromSymbol(out, amcmc::tc_dbg, sizeof(unsigned long long) * 16);
+}
+#endif
