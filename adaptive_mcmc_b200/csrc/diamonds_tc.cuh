@@ -115,4 +115,5 @@ __device__ __forceinline__ float epilogue_sumsq_half(uint32_t taddr) {
   return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+
 }  // namespace amcmc

@@ -16,6 +16,7 @@
 // so the factor is read once and written once per step.  The helper warps run one step ahead and only
 // produce the draws (z, u).
 #include <cmath>
+#include <cstdlib>
 #include <utility>
 #include <vector>
 #include "diamonds_tc.cuh"
@@ -88,6 +89,7 @@ __global__ void tc_mean_finish_kernel(const double* __restrict__ acc, int64_t C,
 //            w = 0, which makes every expression below reproduce the old factor bit for bit, and nothing is stored.
 //   WANT   : accumulate |L' e^lam' - L e^lam|_F^2  (arwmh.py:197)
 //   acc_i  = sum_{j<=i} L~'_ij sqrt(D'_j) zn_j     (zn: next draws in shared memory, stride TC_M; zero if !have_next)
+// (Evict-first hints on the factor stream, ld.cs / st.cs, were measured and make the pass 1.6x slower.)
 // The 351 entries are visited column by column through a ring of TC_RING registers: entry e + TC_RING is requested
 // when entry e is consumed, so TC_RING loads stay in flight per thread for the whole pass (the pass is bound by L2
 // latency, not by bandwidth or issue).  The visit is unrolled at compile time (fold over an index sequence) so the
@@ -235,13 +237,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::OFF_BAR);
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + 2;
-  uint64_t* acc_full = bars + 4;
-  uint64_t* acc_empty = bars + 6;
+  // accumulator hand-off, per stream and TMEM buffer: [stream * 2 + buffer].  Both streams use both buffers; a
+  // waiter on an mbarrier parity may lag at most one phase, so the streams cannot share one barrier ring.
+  uint64_t* acc_full = reinterpret_cast<uint64_t*>(smem + TcSmem::OFF_EXCH);
+  uint64_t* acc_empty = acc_full + 4;
   uint64_t* a_ready = bars + 8;
   uint64_t* v_full = bars + 8 + TC_GR;
   uint64_t* v_empty = bars + 8 + 2 * TC_GR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcSmem::OFF_TMEM);
-  float* sExch = reinterpret_cast<float*>(smem + TcSmem::OFF_EXCH);
   float* sV = reinterpret_cast<float*>(smem + TcSmem::OFF_V);  // [TC_GR][27][TC_M]: next draws z[26], u
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -254,8 +257,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
     for (int s = 0; s < 2; ++s) {
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 32 * TC_EPI_WARPS);
+      mbar_init(&acc_empty[s], 32 * TC_EPI_WARPS / 2);  // the four sampler warps of the owning stream
     }
     for (int g = 0; g < TC_GR; ++g) {
       mbar_init(&a_ready[g], TC_M);
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
 
   const int n_rounds = (g_count + TC_GR - 1) / TC_GR;
   uint32_t x_it = 0, acc_it = 0, a_it = 0;
+  uint32_t ks0 = 0, ks1 = 0;  // MMA warp: accumulators issued so far per stream
 
 #define TC_ROUND_BEGIN                                   \
   for (int rnd = 0; rnd < n_rounds; ++rnd) {             \
@@ -289,7 +295,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
     if (warp == kTmaWarp) {
       TC_ROUND_BEGIN
       if (lane == 0) {  // ===== TMA producer =====
-        for (int64_t st = 0; st < p.n_steps; ++st)
+        const int n_streams = G > 1 ? 2 : 1;  // one sweep over the design matrix per stream and step
+        for (int64_t sweep = 0; sweep < p.n_steps * n_streams; ++sweep)
           for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
             const int s = x_it & 1;
             mbar_wait(&x_empty[s], ((x_it >> 1) & 1) ^ 1);
@@ -303,14 +310,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
       if (lane == 0) {  // ===== MMA issuer =====
         const uint32_t idesc = make_idesc_bf16_f32(TC_M, TC_TILE_N);
         constexpr uint32_t a_kstride = (TC_M / 8) * 128, b_kstride = (TC_TILE_N / 8) * 128;
-        for (int64_t st = 0; st < p.n_steps; ++st) {
+        for (int64_t st = 0; st < p.n_steps; ++st)
+        for (int strm = 0; strm < 2; ++strm) {  // stream = groups strm, strm + 2 (see the sampler warps)
+          if (strm >= G) break;
           for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
             const int s = x_it & 1;
             mbar_wait(&x_full[s], (x_it >> 1) & 1);
-            for (int g = 0; g < G; ++g, ++acc_it) {
+            for (int g = strm; g < G; g += 2) {
               if (tile == 0) mbar_wait(&a_ready[g], (a_it + (uint32_t)st) & 1);
-              const int b = acc_it & 1;
-              mbar_wait(&acc_empty[b], ((acc_it >> 1) & 1) ^ 1);
+              uint32_t& k = strm ? ks1 : ks0;
+              const int b = k & 1;
+              // TMEM buffer b must be drained by its previous users: this stream's accumulator k-2 and, right after a
+              // stream switch, the other stream's last one in this buffer.  uses(s, b) = (k_s + 1 - b) >> 1.
+              const uint32_t u_own = (k + 1 - b) >> 1, u_oth = ((strm ? ks0 : ks1) + 1 - b) >> 1;
+              if (u_own) mbar_wait(&acc_empty[strm * 2 + b], (u_own - 1) & 1);
+              if (u_oth) mbar_wait(&acc_empty[(strm ^ 1) * 2 + b], (u_oth - 1) & 1);
               tc_fence_after();
               const uint32_t a_base = smem_u32(sA + g * TC_A_BYTES), b_base = smem_u32(sX + s * TC_TILE_BYTES);
 #pragma unroll
@@ -319,7 +333,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
                 const uint64_t db = make_smem_desc(b_base + 2 * ks * b_kstride, b_kstride, 128);
                 umma_bf16(tmem_base + (uint32_t)(b * TC_TILE_N), da, db, idesc, ks > 0);
               }
-              umma_commit(&acc_full[b]);
+              umma_commit(&acc_full[strm * 2 + b]);
+              ++k;
             }
             umma_commit(&x_empty[s]);
           }
@@ -359,10 +374,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
       // ===== epilogue / sampler threads =====
       asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSamplerRegs));
       TC_ROUND_BEGIN
+      // Two streams: sampler warps 0-3 own groups 0 and 2, warps 4-7 groups 1 and 3.  The MMA warp serves the
+      // streams alternately, so while one stream's likelihood runs on the tensor cores the other stream's warps
+      // do their accept / factor pass / proposal (HBM- and issue-bound): the two phases overlap.
       const int q4 = warp & 3;
-      const int half = warp >> 2;
+      const int half = warp >> 2;  // stream
       const int row = q4 * 32 + lane;
-      const uint32_t t_lane = ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 128);
+      const uint32_t t_lane = (uint32_t)(q4 * 32) << 16;
+      const int n_mine = G > half ? (G - half + 1) / 2 : 0;
       // The two chains a thread owns (groups 2*half and 2*half+1) are served by ONE copy of the code: the loop
       // over them is rolled and the per-chain scalars are swapped at its end, so they stay in registers.
       float UcurA = 0.f, UcurB = 0.f, maccA = 0.f, maccB = 0.f, lamA = 0.f, lamB = 0.f, uaccA = 2.f, uaccB = 2.f;
@@ -372,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
       int64_t sidx = 0;
 #pragma unroll 1
       for (int rep = 0; rep < 2; ++rep) {
-        const int g = 2 * half + rep;
+        const int g = half + 2 * rep;
         if (g < G) {
           const int64_t c = (int64_t)(g0 + g) * TC_M + row;
           const int64_t cc = c < p.C ? c : (p.C - 1);
@@ -391,34 +410,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
         const int64_t it = p.i0 + st;
         float mine0 = 0.f, mine1 = 0.f;
         if (st >= 0) {
-          float rss[TC_GR];
-#pragma unroll
-          for (int g = 0; g < TC_GR; ++g) rss[g] = 0.f;
-          // ---- likelihood: sum_n m_n^2 from the TMEM accumulators
+          // ---- likelihood: sum_n m_n^2 of this stream's groups from the TMEM accumulators (256 columns each)
           for (int tile = 0; tile < p.n_tiles; ++tile) {
 #pragma unroll
-            for (int g = 0; g < TC_GR; ++g) {
-              if (g < G) {
+            for (int l = 0; l < 2; ++l) {
+              if (l < n_mine) {
                 const int b = acc_it & 1;
-                mbar_wait(&acc_full[b], (acc_it >> 1) & 1);
+                mbar_wait(&acc_full[half * 2 + b], (acc_it >> 1) & 1);
                 tc_fence_after();
-                const float ss = epilogue_sumsq_half(tmem_base + t_lane + (uint32_t)(b * TC_TILE_N));
+                const uint32_t ta = tmem_base + t_lane + (uint32_t)(b * TC_TILE_N);
+                float ss = 0.f;
+#pragma unroll 1
+                for (uint32_t ch = 0; ch < 256u; ch += 128u) ss += epilogue_sumsq_half(ta + ch);  // rolled: 128 live values at a time
                 tc_fence_before();
-                mbar_arrive(&acc_empty[b]);
-                rss[g] += ss;
+                mbar_arrive(&acc_empty[half * 2 + b]);
+                if (l) mine1 += ss; else mine0 += ss;
                 ++acc_it;
               }
             }
           }
-#pragma unroll
-          for (int g = 0; g < TC_GR; ++g)
-            if (g < G && (g >> 1) != half) sExch[g * TC_M + row] = rss[g];
           TC_T(1);
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
-          const float own0 = half ? rss[2] : rss[0], own1 = half ? rss[3] : rss[1];
-          if (2 * half < G) mine0 = own0 + sExch[(2 * half) * TC_M + row];
-          if (2 * half + 1 < G) mine1 = own1 + sExch[(2 * half + 1) * TC_M + row];
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
           TC_T(2);
         }
         bool collect_now = false;
@@ -432,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
         const float gamma_n = (n == 1) ? 1.f : Num<float>::pow_neg(nf, ap.lr_decay);
 #pragma unroll 1
         for (int rep = 0; rep < 2; ++rep) {
-          const int g = 2 * half + rep;
+          const int g = half + 2 * rep;
           if (g < G) {
             const int64_t c = (int64_t)(g0 + g) * TC_M + row;
             const bool live = c < p.C;
@@ -532,7 +543,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
       // ---- write back the per-chain scalars and the position if it ended in the shadow buffer
 #pragma unroll 1
       for (int rep = 0; rep < 2; ++rep) {
-        const int g = 2 * half + rep;
+        const int g = half + 2 * rep;
         if (g < G) {
           const int64_t c = (int64_t)(g0 + g) * TC_M + row;
           if (c < p.C) {
@@ -598,6 +609,10 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (const char* cap = getenv("AMCMC_TC_MAX_CTAS")) {  // test hook: several groups / rounds per CTA at small chain counts
+    const int v = atoi(cap);
+    if (v > 0 && v < sms) sms = v;
+  }
   const int grid = ap.p.n_groups < sms ? ap.p.n_groups : sms;
   if (a->rng_mode == AMCMC_RNG_EXTERNAL) {
     if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_adapt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;

@@ -232,9 +232,14 @@ def test_diamonds_tc_adaptive_matches_oracle(C, diamonds_data):
     assert int(last.i) == T
 
 
-def test_diamonds_tc_adaptive_matches_block_kernel(diamonds_data):
-    """Philox draws: the tensor-core adaptive path and the exact CUDA-core block kernel run the same chains."""
-    C, d, T = 512, 26, 30
+@pytest.mark.parametrize("C,max_ctas", [(512, 0), (512, 1), (1000, 1), (1000, 3), (700, 2)])
+def test_diamonds_tc_adaptive_matches_block_kernel(C, max_ctas, diamonds_data, monkeypatch):
+    """Philox draws: the tensor-core adaptive path and the exact CUDA-core block kernel run the same chains.
+    `max_ctas` caps the grid (AMCMC_TC_MAX_CTAS) so that a CTA serves 2-4 chain groups, in one or two rounds, in
+    two alternating streams -- the situation of 65,536 chains on 148 SMs -- at a chain count the test can afford."""
+    if max_ctas:
+        monkeypatch.setenv("AMCMC_TC_MAX_CTAS", str(max_ctas))
+    d, T = 26, 30
     rng = np.random.default_rng(8)
     q0 = _mode(diamonds_data)[None] + 0.004 * rng.normal(size=(C, d))
     res = {}
