@@ -97,6 +97,10 @@ EXPORTED_SYMBOLS = (
     "amcmc_pooled_stats",
     "amcmc_pooled_update",
     "amcmc_selftest_umma",
+    "amcmc_eval_kernel_sum",
+    "amcmc_eval_sqdist_median",
+    "amcmc_eval_cost_matrix",
+    "amcmc_eval_moment",
     "amcmc_last_error",
     "amcmc_version",
 )
@@ -146,6 +150,15 @@ def lib():
     L.amcmc_pooled_update.argtypes = [C.POINTER(AmcmcPooled), C.c_void_p, C.c_double, C.c_double, C.c_void_p]
     L.amcmc_selftest_umma.restype = C.c_int
     L.amcmc_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.amcmc_eval_kernel_sum.restype = C.c_int
+    L.amcmc_eval_kernel_sum.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int,
+                                        C.POINTER(C.c_double), C.c_void_p]
+    L.amcmc_eval_sqdist_median.restype = C.c_int
+    L.amcmc_eval_sqdist_median.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_double), C.c_void_p]
+    L.amcmc_eval_cost_matrix.restype = C.c_int
+    L.amcmc_eval_cost_matrix.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    L.amcmc_eval_moment.restype = C.c_int
+    L.amcmc_eval_moment.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_void_p]
     _lib = L
     return L
 

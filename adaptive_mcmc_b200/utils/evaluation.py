@@ -1,0 +1,156 @@
+"""Sample-quality metrics -- the reference's ``python/utils/evaluation.py`` on the GPU.
+
+Same function names, argument meaning and return values (Python floats).  Inputs are ``[n, d]`` sample arrays
+(torch tensors on any device, or NumPy); they are moved to the GPU as float32, the dtype the reference computes
+in.  The all-pairs passes (kernel sums, median heuristic, cost matrix) and the moment estimates are hand-written
+CUDA behind the C ABI (``csrc/eval.cu``); nothing of size n*m is materialised except the assignment cost matrix.
+
+Not provided: ``wasserstein_sinkhorn`` / ``wasserstein_sinkhorn_unbiased`` (evaluation.py:64-126) -- they delegate
+to the OTT-JAX solver (``ott.solvers.linear.solve`` with its default epsilon schedule and stopping rule), which is
+not in this image and whose result is defined by that implementation, not by the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def _dev(x, device=None):
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(np.asarray(x))
+    if x.dim() == 1:
+        x = x[:, None]
+    if x.dim() != 2:
+        raise ValueError("samples must be [n, d]")
+    if device is None:
+        device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return x.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _kernel_sum(x, y, gamma, skip_diagonal=False):
+    out = C.c_double(0.0)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().amcmc_eval_kernel_sum(x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0], x.shape[1], float(gamma),
+                                                    int(skip_diagonal), C.byref(out), _stream(x)), "amcmc_eval_kernel_sum")
+    return out.value
+
+
+def sqdist_median(y):
+    """median_ij |y_i - y_j|^2 over the full m x m matrix (the argument of the median heuristic, evaluation.py:283)."""
+    y = _dev(y)
+    out = C.c_double(0.0)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.lib().amcmc_eval_sqdist_median(y.data_ptr(), y.shape[0], y.shape[1], C.byref(out), _stream(y)),
+                   "amcmc_eval_sqdist_median")
+    return out.value
+
+
+def _moment(x, p):
+    out = (C.c_double * x.shape[1])()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().amcmc_eval_moment(x.data_ptr(), x.shape[0], x.shape[1], float(p), out, _stream(x)), "amcmc_eval_moment")
+    return np.array(out[:], dtype=np.float64)
+
+
+def pth_moment_rmse(x, y, p=2.0):
+    """evaluation.py:13-38: |mean(x**p, 0) - mean(y**p, 0)|_2."""
+    x = _dev(x)
+    y = _dev(y, x.device)
+    if x.shape[1] != y.shape[1]:
+        raise ValueError("x and y must have the same dimension")
+    return float(np.linalg.norm(_moment(x, p) - _moment(y, p)))
+
+
+def cost_matrix(u_values, v_values, ord=2.0):
+    """scipy.spatial.distance_matrix(u, v, p=ord) as a CUDA tensor [n, m]."""
+    u = _dev(u_values)
+    v = _dev(v_values, u.device)
+    if u.shape[1] != v.shape[1]:
+        raise ValueError("u and v must have the same dimension")
+    out = torch.empty(u.shape[0], v.shape[0], dtype=torch.float32, device=u.device)
+    with torch.cuda.device(u.device):
+        _lib.check(_lib.lib().amcmc_eval_cost_matrix(u.data_ptr(), u.shape[0], v.data_ptr(), v.shape[0], u.shape[1], float(ord),
+                                                     out.data_ptr(), _stream(u)), "amcmc_eval_cost_matrix")
+    return out
+
+
+def wasserstein_dist11_p(u_values, v_values, ord=2.0):
+    """evaluation.py:41-62: mean cost of the optimal 1-1 coupling.  The cost matrix is built on the GPU; the
+    assignment itself is the reference's own host call (scipy.optimize.linear_sum_assignment)."""
+    from scipy.optimize import linear_sum_assignment
+
+    cm = cost_matrix(u_values, v_values, ord).cpu().numpy()
+    row_ind, col_ind = linear_sum_assignment(cm)
+    return float(cm[row_ind, col_ind].mean())
+
+
+def wasserstein_1d(mu, nu, p=1.0):
+    """evaluation.py:129-154: (mean |sort(mu) - sort(nu)|^p)^(1/p) along the last axis."""
+    mu = torch.as_tensor(mu, dtype=torch.float32)
+    nu = torch.as_tensor(nu, dtype=torch.float32).to(mu.device)
+    diff = (torch.sort(mu, dim=-1).values - torch.sort(nu, dim=-1).values).abs()
+    return (diff ** p).mean(dim=-1) ** (1.0 / p)
+
+
+def max_sliced_wasserstein(mu, nu, rng_key, p=1.0, n_directions=1000):
+    """evaluation.py:158-198: max over random unit directions of the 1-D Wasserstein-p distance of the projections.
+    `rng_key`: int seed or 2-word key; the directions come from torch's Philox generator, not from JAX's threefry,
+    so the value agrees with the reference in distribution, not draw for draw."""
+    mu = _dev(mu)
+    nu = _dev(nu, mu.device)
+    key = np.asarray(rng_key.cpu() if isinstance(rng_key, torch.Tensor) else rng_key).astype(np.uint64).ravel()
+    seed = int(key[-1]) if key.size else 0
+    g = torch.Generator(device=mu.device)
+    g.manual_seed(seed)
+    dirs = torch.randn(n_directions, mu.shape[1], generator=g, device=mu.device, dtype=torch.float32)
+    dirs = dirs / torch.linalg.norm(dirs, dim=1, keepdim=True)
+    best = 0.0
+    for blk in torch.split(dirs, 256):  # [b, d] x [d, n]: bounded workspace
+        dist = wasserstein_1d(blk @ mu.t(), blk @ nu.t(), p=p)
+        best = max(best, float(dist.max()))
+    return best
+
+
+def gaussian_kernel_sum(x, y, gamma, skip_diagonal=False):
+    """sum(gaussian_kernel(x, y, gamma)) (evaluation.py:201-222) without the n x m matrix."""
+    x = _dev(x)
+    y = _dev(y, x.device)
+    if x.shape[1] != y.shape[1]:
+        raise ValueError("x and y must have the same dimension")
+    return _kernel_sum(x, y, gamma, skip_diagonal)
+
+
+def mmd2_unbiased(x, y, gamma=1.0):
+    """evaluation.py:225-263."""
+    x = _dev(x)
+    y = _dev(y, x.device)
+    n, m = x.shape[0], y.shape[0]
+    return (_kernel_sum(x, x, gamma, True) / (n * (n - 1)) + _kernel_sum(y, y, gamma, True) / (m * (m - 1))
+            - 2.0 * _kernel_sum(x, y, gamma) / (n * m))
+
+
+def mmd_heuristic(x, y):
+    """evaluation.py:266-294: biased MMD with the median-heuristic bandwidth gamma = 4 / median |y_i - y_j|^2."""
+    x = _dev(x)
+    y = _dev(y, x.device)
+    n, m = x.shape[0], y.shape[0]
+    gamma = 4.0 / sqdist_median(y)
+    mmd2 = _kernel_sum(x, x, gamma) / n**2 + _kernel_sum(y, y, gamma) / m**2 - 2.0 * _kernel_sum(x, y, gamma) / (n * m)
+    return math.sqrt(mmd2) if mmd2 >= 0 else float("nan")  # jnp.sqrt of a round-off negative is nan in the reference too
+
+
+def wasserstein_sinkhorn(*args, **kwargs):
+    raise NotImplementedError("wasserstein_sinkhorn delegates to the OTT-JAX solver in the reference (evaluation.py:64-97); "
+                              "OTT-JAX is not available here and its result is defined by that implementation")
+
+
+wasserstein_sinkhorn_unbiased = wasserstein_sinkhorn

@@ -183,6 +183,25 @@ int amcmc_pooled_update(amcmc_pooled* pool, const double* stats, double lr_decay
 int amcmc_selftest_umma(const void* a_bf16, const void* b_bf16, int K, void* scratch, float* d_out, int use_tma,
                         int swap_lbo_sbo, void* stream);
 
+/* ---- sample-quality metrics (python/utils/evaluation.py), SURVEY 8f rank 4 ------------------------------------
+ * Samples are row-major [n][d] float32 DEVICE arrays, like the reference's jnp arrays.  Functions with an
+ * `out_host` argument write HOST memory and synchronise `stream` before returning. */
+
+/* sum_ij exp(-gamma |x_i - y_j|^2): the three sums of mmd_heuristic (evaluation.py:286-291) and, with
+ * skip_diagonal != 0 (x == y), the off-diagonal sums of mmd2_unbiased (:251-261).  Replaces gaussian_kernel(...).sum()
+ * (:201-222) without materialising the n x m matrix. */
+int amcmc_eval_kernel_sum(const float* x, int64_t n, const float* y, int64_t m, int d, double gamma, int skip_diagonal,
+                          double* out_host, void* stream);
+/* Median of all m*m squared pairwise distances of y (diagonal zeros and both orders included): the bandwidth
+ * heuristic gamma = 4 / median (evaluation.py:283).  Exact radix select on the float32 keys, no m*m buffer. */
+int amcmc_eval_sqdist_median(const float* y, int64_t m, int d, double* out_host, void* stream);
+/* out[i*m + j] = |x_i - y_j|_ord (ord >= 1): scipy.spatial.distance_matrix(u, v, p=ord) of wasserstein_dist11_p
+ * (evaluation.py:58).  `out` is a DEVICE array; asynchronous on `stream`. */
+int amcmc_eval_cost_matrix(const float* x, int64_t n, const float* y, int64_t m, int d, double ord, float* out,
+                           void* stream);
+/* out_host[k] = mean_i x_ik^p, k < d: the moment estimates of pth_moment_rmse (evaluation.py:33-34). */
+int amcmc_eval_moment(const float* x, int64_t n, int d, double p, double* out_host, void* stream);
+
 const char* amcmc_last_error(void);
 int amcmc_version(void);
 

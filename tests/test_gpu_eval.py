@@ -1,0 +1,98 @@
+"""Sample-quality metrics on the GPU (csrc/eval.cu through the C ABI) against the NumPy restatement of
+python/utils/evaluation.py, plus size-independent properties at the reference's sample count (10^4)."""
+import numpy as np
+import pytest
+import torch
+
+from adaptive_mcmc_b200.utils import evaluation as ev
+from oracle import evaluation_numpy as oe
+
+pytestmark = pytest.mark.gpu
+
+
+def _samples(n, m, d, seed, shift=0.3):
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(d, d)) / np.sqrt(d)
+    x = (rng.normal(size=(n, d)) @ A).astype(np.float32)
+    y = (rng.normal(size=(m, d)) @ A + shift).astype(np.float32)
+    return x, y
+
+
+@pytest.mark.parametrize("n,m,d", [(300, 257, 10), (129, 400, 26), (64, 64, 4), (50, 33, 1), (200, 130, 70)])
+def test_kernel_sums_and_median_match_oracle(n, m, d):
+    x, y = _samples(n, m, d, seed=n + d)
+    # median of the full m x m squared-distance matrix: the GPU select is exact on ITS float32 distances; the
+    # oracle's differ in the last bits (summation order), so compare to float32 rounding of a d-term sum
+    med_g, med_o = ev.sqdist_median(y), oe.median_sqdist(y)
+    assert abs(med_g - med_o) <= 4e-6 * med_o + 1e-12
+    for gamma in (4.0 / med_o, 1.0):
+        for (a, b) in ((x, x), (y, y), (x, y)):
+            s_g = ev.gaussian_kernel_sum(a, b, gamma)
+            s_o = float(oe.gaussian_kernel(a, b, gamma).sum(dtype=np.float64))
+            assert abs(s_g - s_o) <= 2e-6 * s_o + 1e-9, (gamma, s_g, s_o)
+    assert abs(ev.mmd_heuristic(x, y) - oe.mmd_heuristic(x, y)) < 2e-5
+    assert abs(ev.mmd2_unbiased(x, y, gamma=0.7) - oe.mmd2_unbiased(x, y, gamma=0.7)) < 2e-6
+
+
+@pytest.mark.parametrize("m", [7, 8, 31])
+def test_median_even_and_odd_counts(m):
+    # m*m odd -> one middle element; even -> mean of the two middle ones (jnp.median)
+    y = _samples(3, m, 5, seed=m)[1]
+    assert abs(ev.sqdist_median(y) - oe.median_sqdist(y)) <= 4e-6 * oe.median_sqdist(y)
+
+
+@pytest.mark.parametrize("ord", [1.0, 2.0, 3.0])
+def test_cost_matrix_and_assignment(ord):
+    x, y = _samples(150, 150, 10, seed=5)
+    cm = ev.cost_matrix(x, y, ord).cpu().numpy()
+    ref = oe.distance_matrix(x, y, ord)
+    np.testing.assert_allclose(cm, ref, rtol=3e-6, atol=1e-6)
+    assert abs(ev.wasserstein_dist11_p(x, y, ord) - oe.wasserstein_dist11_p(x, y, ord)) < 1e-5
+
+
+def test_moment_rmse():
+    x, y = _samples(5000, 3000, 26, seed=2)
+    for p in (1.0, 2.0, 3.0):
+        assert abs(ev.pth_moment_rmse(x, y, p) - oe.pth_moment_rmse(x, y, p)) < 5e-6 * max(1.0, oe.pth_moment_rmse(x, y, p))
+
+
+def test_sliced_wasserstein():
+    x, y = _samples(2000, 2000, 10, seed=9)
+    # the 1-D distance itself
+    a, b = x[:, 0], y[:, 0]
+    assert abs(float(ev.wasserstein_1d(torch.from_numpy(a), torch.from_numpy(b), p=2.0)) - float(oe.wasserstein_1d(a, b, 2.0))) < 1e-6
+    v = ev.max_sliced_wasserstein(x, y, rng_key=[0, 3], p=1.0, n_directions=500)
+    # a pure shift of 0.3 per coordinate: the max-sliced W1 is close to the shift along (1,..,1)/sqrt(d), and never above it by much
+    assert 0.5 * 0.3 * np.sqrt(10) < v < 1.2 * 0.3 * np.sqrt(10), v
+    assert ev.max_sliced_wasserstein(x, x, rng_key=1, n_directions=50) == 0.0
+
+
+def test_full_size_properties():
+    """n = m = 10^4, d = 26 (posteriordb reference-draw count): identities that need no oracle."""
+    x, y = _samples(10000, 10000, 26, seed=1, shift=0.05)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    same = ev.mmd_heuristic(xt, xt)
+    assert same != same or same < 2e-3               # sqrt of round-off around an exact zero (nan if it lands below)
+    a, b = ev.mmd_heuristic(xt, yt), ev.mmd_heuristic(yt[torch.randperm(10000, device="cuda")], yt)
+    assert a > 0.01 and (b != b or a > 5 * b)        # a shifted sample is far, a permutation of y is not
+    g = 4.0 / ev.sqdist_median(yt)
+    sxy, syx = ev.gaussian_kernel_sum(xt, yt, g), ev.gaussian_kernel_sum(yt, xt, g)
+    assert abs(sxy - syx) < 1e-9 * sxy               # symmetric
+    # against a float64 torch evaluation of the same sum
+    ref = torch.exp(-g * torch.cdist(xt.double(), yt.double()) ** 2).sum().item()
+    assert abs(sxy - ref) < 3e-6 * ref
+    # the median against torch on the float64 distances
+    med = torch.median((torch.cdist(yt[:3000].double(), yt[:3000].double()) ** 2).flatten()).item()
+    assert abs(ev.sqdist_median(yt[:3000]) - med) < 1e-5 * med
+    # diagonal-free sum = full sum - n
+    assert abs(ev.gaussian_kernel_sum(xt, xt, g, skip_diagonal=True) - (ev.gaussian_kernel_sum(xt, xt, g) - 10000)) < 1e-3
+
+
+def test_argument_errors():
+    x, y = _samples(10, 10, 3, seed=0)
+    with pytest.raises(ValueError):
+        ev.gaussian_kernel_sum(x, y[:, :2], 1.0)
+    with pytest.raises(ValueError):
+        ev.cost_matrix(x, y, ord=0.5)
+    with pytest.raises(NotImplementedError):
+        ev.wasserstein_sinkhorn(x, y)

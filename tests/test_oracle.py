@@ -228,3 +228,26 @@ def test_ess_and_rhat():
     assert 0.8 * expect < ess < 1.2 * expect
     assert abs(o.split_gelman_rubin(x) - 1) < 0.01
     assert o.split_gelman_rubin(x + np.arange(4)[:, None]) > 1.3
+
+
+# ---- sample-quality metrics oracle (python/utils/evaluation.py) --------------------------------------------
+def test_evaluation_oracle_identities():
+    from oracle import evaluation_numpy as oe
+    from scipy.stats import wasserstein_distance
+
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(200, 5)).astype(np.float32)
+    y = (rng.normal(size=(150, 5)) + 0.5).astype(np.float32)
+    # independent formula for the kernel sum: |x|^2 + |y|^2 - 2 x.y in float64
+    d2 = (x.astype(np.float64) ** 2).sum(1)[:, None] + (y.astype(np.float64) ** 2).sum(1)[None] - 2 * x.astype(np.float64) @ y.astype(np.float64).T
+    np.testing.assert_allclose(oe.sqdist(x, y), d2, rtol=2e-5, atol=1e-5)
+    assert oe.mmd_heuristic(x, x) < 1e-3
+    assert oe.mmd_heuristic(x, y) > 0.1
+    # mmd2_unbiased has zero mean under the null: two halves of one sample give a value near 0 (either sign)
+    assert abs(oe.mmd2_unbiased(x[:100], x[100:], 0.5)) < 0.02
+    # 1-D Wasserstein against SciPy
+    a, b = x[:, 0], y[:200 - 50, 0]
+    assert abs(float(oe.wasserstein_1d(a[:150], b, 1.0)) - wasserstein_distance(a[:150], b)) < 1e-6
+    # the 1-1 coupling of a sample with a shifted copy of itself costs exactly the shift
+    assert abs(oe.wasserstein_dist11_p(x[:60], x[:60] + np.float32(0.25), 2.0) - 0.25 * np.sqrt(5)) < 1e-5
+    assert abs(oe.pth_moment_rmse(x, x, 2.0)) == 0.0
