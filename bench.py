@@ -570,8 +570,9 @@ def run_diamonds_adaptive(args, world, rank, dev, K, W):
             "achieved": per_gpu * 240000 * 3 / 1e12, "frac": per_gpu * 240000 * 3 / 1e12 / tpeak,
             "state_stream_GBps": per_gpu * state_bytes / 1e9, "state_stream_frac_of_hbm": per_gpu * state_bytes / 1e9 / hpeak,
             "traffic": _traffic("diamonds_tc_adaptive"),
-            "note": f"two serial phases per step: the tensor-core likelihood and the per-chain state pass ({state_bytes} B "
-                    "per chain-step, L2-resident at 65,536 chains); the step time is their sum, so neither fraction can reach 1",
+            "note": f"two alternating streams per SM overlap the tensor-core likelihood with the per-chain state pass ({state_bytes} B "
+                    "per chain-step, re-streamed from HBM every step at 65,536 chains); bound by SM<->L2 traffic (3.3 MB per step "
+                    "and SM), see profiles/r01_diamonds_tc_adaptive.md",
         },
     }
 
