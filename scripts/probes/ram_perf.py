@@ -1,0 +1,13 @@
+import numpy as np, torch, sys, time
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import adaptive_mcmc_b200 as am
+from adaptive_mcmc_b200 import models
+d,C=200,16384
+P=models.ar1_precision_chol(d,0.9)
+s=am.RAM(models.gaussian,num_chains=C,init_strategy=am.init_to_value(torch.zeros(C,d)))
+st=s.init(3,num_warmup=0,init_params=None,model_kwargs=dict(prec_chol=P))
+b=am.ChainBatch.from_state(s.potential,st,copy=False)
+for T in (100,100,400):
+    torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+    e0.record(); s.run_batch(b,T,collect=()); e1.record(); torch.cuda.synchronize()
+    ms=e0.elapsed_time(e1); print(T,'steps', ms,'ms', '%.3g chain-steps/s'%(C*T/ms*1e3), 'acc', float(b.macc.mean()))

@@ -205,7 +205,7 @@ def test_diamonds_tc_adaptive_matches_oracle(C, diamonds_data):
     a, oa_ = last.adapt_state, olast.adapt_state
     # The posterior is sharp (sd ~ 0.002 per coordinate) and the step is chaotic in the energies: the ~1e-3 absolute
     # error of fp32 energies enters lambda through gamma*(alpha - target), lambda scales the next proposal, and the
-    # difference grows ~40x over these 40 steps (scratch/tc_adapt_diag.py prints the growth curve).  So the adapted
+    # difference grows ~40x over these 40 steps (scripts/probes/tc_adapt_diag.py prints the growth curve).  So the adapted
     # state is compared chain by chain: nearly all chains inside the tight band, every chain inside a loose one.
     def close(x, y, rtol, atol):
         x = np.asarray(x.cpu().numpy() if hasattr(x, "cpu") else x, np.float64)[same].reshape(int(same.sum()), -1)
