@@ -450,6 +450,8 @@ void destroy_diamonds_tc(amcmc_model* m) {
   if (ex->ident) cudaFree(ex->ident);
   if (ex->zero) cudaFree(ex->zero);
   if (ex->ldl) cudaFree(ex->ldl);
+  if (ex->cref) cudaFree(ex->cref);
+  if (ex->crss) cudaFree(ex->crss);
   free(ex);
   m->extra = nullptr;
 }

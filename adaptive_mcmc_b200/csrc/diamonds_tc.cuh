@@ -46,6 +46,9 @@ struct DiamondsTcExtra {
   float* zero;       // [1]
   float* ldl;        // [ldl_groups][351][128] per-chain LDL^T factors of the adaptive path (see diamonds_tc_adapt.cu)
   int64_t ldl_groups;
+  float* cref;       // [50][cref_cap] per-chain GEMM reference: rows 0-24 q_ref, rows 25-49 2 g
+  double* crss;      // [cref_cap] RSS at the reference point
+  int64_t cref_cap;
 };
 
 struct TcParams {

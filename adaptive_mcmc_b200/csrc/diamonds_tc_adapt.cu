@@ -27,6 +27,8 @@ struct TcAdaptParams {
   TcParams p;        // chains, tiles, positions, energies, draws, outputs (as the shared-state kernel)
   float* loc;        // [26][C]
   float* ldl;        // [n_groups][351][128]  LDL^T blocks
+  const float* cref; // [50][C] per-chain reference point of the centred GEMM: q_ref (25), 2 g (25)
+  const double* crss;  // [C] RSS at the reference point
   float* lam;        // [C]
   float* asc;        // [C]
   int64_t num_warmup;
@@ -66,22 +68,39 @@ __global__ void tc_ldl_to_chol_kernel(const float* __restrict__ ldl, float* __re
   }
 }
 
-// mean position over the chains -> reference point of the centred GEMM (float64 atomics, 26 values)
-__global__ void tc_mean_kernel(const float* __restrict__ z, int64_t C, double* __restrict__ acc) {
-  const int k = blockIdx.y;
-  double s = 0;
-  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (int64_t)gridDim.x * blockDim.x)
-    s += (double)z[(int64_t)k * C + c];
+// Per-chain reference point of the centred GEMM (see diamonds_tc.cu for the formulation): q_ref = the chain's own
+// position at the start of the segment, g = X1^T r_ref = h - G q_ref and RSS_ref = yy - 2 h.q + q.G q from the float64
+// Gram matrix.  With its own reference a chain only ever sends its displacement SINCE THE SEGMENT START through the
+// split-bf16 GEMM, so the accuracy of the energies does not depend on how far the batch is spread (chains that start
+// at U(-2,2)^26 sit at |U| ~ 1e4-1e6 for tens of thousands of steps; a shared reference costs 30x accuracy there).
+__global__ void tc_chain_ref_kernel(const double* __restrict__ gram, const float* __restrict__ z, int64_t C, float* __restrict__ cref,
+                                    double* __restrict__ crss) {
+  __shared__ double sG[TC_KC * TC_KC + TC_KC + 1];
+  for (int e = threadIdx.x; e < TC_KC * TC_KC + TC_KC + 1; e += blockDim.x) sG[e] = gram[e];
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* h = sG + TC_KC * TC_KC;
+  double q[TC_KC];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&acc[k], s);
-}
-__global__ void tc_mean_finish_kernel(const double* __restrict__ acc, int64_t C, float* __restrict__ loc, float* __restrict__ ident,
-                                      float* __restrict__ zero) {
-  const int t = threadIdx.x;
-  if (t < TC_D) loc[t] = (float)(acc[t] / (double)C);
-  for (int e = t; e < TC_NP; e += blockDim.x) ident[e] = 0.f;
-  if (t == 0) zero[0] = 0.f;
+  for (int k = 0; k < TC_KC; ++k) {
+    const float v = z[(int64_t)k * C + c];
+    q[k] = (double)v;
+    cref[(int64_t)k * C + c] = v;
+  }
+  double rss = sG[TC_KC * TC_KC + TC_KC];
+#pragma unroll 1
+  for (int a = 0; a < TC_KC; ++a) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < TC_KC; ++k) s = fma(sG[a * TC_KC + k], q[k], s);
+    cref[(int64_t)(TC_KC + a) * C + c] = (float)(2.0 * (h[a] - s));
+    double qa = 0.0;  // q[a] with a runtime index: select instead of indexing (keeps q in registers)
+#pragma unroll
+    for (int k = 0; k < TC_KC; ++k) qa = (k == a) ? q[k] : qa;
+    rss = fma(qa, s - 2.0 * h[a], rss);
+  }
+  crss[c] = rss;
 }
 
 // One pass over the chain's LDL^T factor in global memory (see the file header).
@@ -174,14 +193,21 @@ __device__ __forceinline__ float tc_column_pass(float* __restrict__ col, const f
 }
 
 // proposal -> A' row (split bf16), scalar part of U', shadow position buffer.  Returns via references.
-__device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const float* sRef, unsigned char* sA, int g, int row,
-                                                 uint64_t* a_ready_g, double n_rows, double cst, double& Up_part, double& inv2var) {
+__device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const float* __restrict__ cref, int64_t C, double rss_ref,
+                                                 unsigned char* sA, int g, int row, uint64_t* a_ready_g, double n_rows, double cst,
+                                                 double& Up_part, double& inv2var) {
   float dq = 0.f;
   uint32_t hi[TC_KC], lo[TC_KC];  // bf16 bit patterns in the low halves
+  float qr[TC_KC], g2[TC_KC];
+#pragma unroll
+  for (int k = 0; k < TC_KC; ++k) {  // this chain's reference point and gradient (coalesced over the group)
+    qr[k] = __ldg(cref + (int64_t)k * C);
+    g2[k] = __ldg(cref + (int64_t)(TC_KC + k) * C);
+  }
 #pragma unroll
   for (int k = 0; k < TC_KC; ++k) {
-    const float dlt = xp[k] - sRef[REF_Q + k];
-    dq = fmaf(dlt, sRef[REF_G2 + k], dq);
+    const float dlt = xp[k] - qr[k];
+    dq = fmaf(dlt, g2[k], dq);
     const uint16_t h = f2bf(dlt);
     hi[k] = h;
     lo[k] = f2bf(dlt - bf2f(h));
@@ -209,12 +235,13 @@ __device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const 
   const float ti = (xp[0] - 8.f) * 0.1f, ts = __expf(s) * 0.1f;
   inv2var = 0.5 * exp(-2.0 * (double)s);
   Up_part = (double)(0.5f * sb + 2.f * log1pf(ti * ti * (1.f / 3.f)) + 2.f * log1pf(ts * ts * (1.f / 3.f))) +
-            (n_rows - 1.0) * (double)s + cst + inv2var * (*reinterpret_cast<const double*>(sRef + REF_RSS) - (double)dq);
+            (n_rows - 1.0) * (double)s + cst + inv2var * (rss_ref - (double)dq);
 }
 
 // Warp roles: warps 0-7 = the two sampler warpgroups (TMEM epilogue + per-chain state), warp 8 = TMA producer,
 // warp 9 = MMA issuer, warps 10-11 = draws.  The sampler warpgroups take the registers the third one gives up
 // (setmaxnreg: 2 x 128 x 208 + 128 x 88 = 384 x 168, the CTA's pool at launch), which is what keeps the unrolled column pass spill-free.
+constexpr int64_t kSegment = 256;  // steps between moves of the GEMM reference point
 constexpr int kTmaWarp = TC_EPI_WARPS, kMmaWarp = TC_EPI_WARPS + 1;
 constexpr int kSamplerRegs = 208, kServiceRegs = 88, kLaunchRegs = 168;  // launch: 65536 / 384 rounded down to 8
 static_assert(TC_EPI_WARPS == 8 && TC_HELP_WARPS == 2, "warp roles assume 8 sampler + 4 service warps");
@@ -233,7 +260,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* sX = smem + TcSmem::OFF_X;
   unsigned char* sA = smem + TcSmem::OFF_A;
-  float* sRef = reinterpret_cast<float*>(smem + TcSmem::OFF_REF);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::OFF_BAR);
   uint64_t* x_full = bars;
   uint64_t* x_empty = bars + 2;
@@ -270,7 +296,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
-  for (int e = tid; e < REF_FLOATS; e += TC_THREADS) sRef[e] = p.ref[e];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -523,7 +548,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
               }
               uaccA = zn[26 * TC_M];
               mbar_arrive(&v_empty[g]);
-              tc_emit_proposal(xp, sRef, sA, g, row, &a_ready[g], (double)p.n_rows, p.cst, UppA, i2vA);
+              tc_emit_proposal(xp, ap.cref + cc, p.C, ap.crss[cc], sA, g, row, &a_ready[g], (double)p.n_rows, p.cst, UppA, i2vA);
               TC_T(6);
             }
           }
@@ -592,11 +617,6 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
   ap.target = (float)a->target_accept_prob;
   ap.eps = (float)a->eps;
   const int64_t C = st->n_chains;
-  // reference point of the centred GEMM = current mean position of the batch
-  if ((rc = check_cuda(cudaMemsetAsync(ex->mean_acc, 0, sizeof(double) * 32, s), "cudaMemsetAsync"))) return rc;
-  tc_mean_kernel<<<dim3(64, TC_D), 256, 0, s>>>((const float*)st->z, C, ex->mean_acc);
-  tc_mean_finish_kernel<<<1, 128, 0, s>>>(ex->mean_acc, C, ex->qmean, ex->ident, ex->zero);
-  diamonds_tc_launch_ref(m, ex->qmean, ex->ident, ex->zero, 0.0, s);
   if (ex->ldl_groups < ap.p.n_groups) {
     if (ex->ldl) cudaFree(ex->ldl);
     ex->ldl = nullptr;
@@ -605,6 +625,16 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     ex->ldl_groups = ap.p.n_groups;
   }
   ap.ldl = ex->ldl;
+  if (ex->cref_cap < C) {
+    if (ex->cref) cudaFree(ex->cref);
+    if (ex->crss) cudaFree(ex->crss);
+    ex->cref = nullptr; ex->crss = nullptr; ex->cref_cap = 0;
+    if ((rc = check_cuda(cudaMalloc(&ex->cref, (size_t)C * 2 * TC_KC * sizeof(float)), "cudaMalloc(cref)"))) return rc;
+    if ((rc = check_cuda(cudaMalloc(&ex->crss, (size_t)C * sizeof(double)), "cudaMalloc(crss)"))) return rc;
+    ex->cref_cap = C;
+  }
+  ap.cref = ex->cref;
+  ap.crss = ex->crss;
   tc_chol_to_ldl_kernel<<<ap.p.n_groups, TC_M, 0, s>>>((const float*)st->scale, ap.ldl, C);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -614,14 +644,37 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     if (v > 0 && v < sms) sms = v;
   }
   const int grid = ap.p.n_groups < sms ? ap.p.n_groups : sms;
-  if (a->rng_mode == AMCMC_RNG_EXTERNAL) {
-    if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_adapt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
-    diamonds_tc_adapt_kernel<true><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
-  } else {
-    if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_adapt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
-    diamonds_tc_adapt_kernel<false><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
+  if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_adapt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
+  if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_adapt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
+  // The centred GEMM is accurate while a chain is close to its reference point (the cancellation in
+  // RSS_ref - 2 d.g + sum m^2 grows with |d|^2), so the run is cut into segments of at most kSegment steps and every
+  // chain's reference point is moved to its current position before each of them.  Per-chain state stays in the
+  // LDL^T blocks across the segments.
+  const TcParams full = ap.p;
+  int64_t seg = kSegment;
+  if (const char* e = getenv("AMCMC_TC_SEGMENT")) {  // test hook: exercise the segment bookkeeping in short runs
+    const long v = atol(e);
+    if (v > 0) seg = v;
   }
-  if ((rc = check_cuda(cudaGetLastError(), "diamonds_tc_adapt_kernel launch"))) return rc;
+  for (int64_t s0 = 0; s0 < full.n_steps; s0 += seg) {
+    TcParams& p = ap.p;
+    p = full;
+    p.i0 = full.i0 + s0;
+    p.n_steps = full.n_steps - s0 < seg ? full.n_steps - s0 : seg;
+    // sample bookkeeping of the segment: steps until the next kept sample, index of that sample
+    const int64_t r = s0 - full.collect_start;
+    const int64_t kept = r <= 0 ? 0 : r / full.thinning;
+    p.collect_start = r <= 0 ? -r : -(r % full.thinning);
+    if (full.out_z) p.out_z = full.out_z + kept * TC_D * C;
+    if (full.out_pe) p.out_pe = full.out_pe + kept * C;
+    if (full.out_acc) p.out_acc = full.out_acc + s0 * C;
+    if (full.normals) p.normals = full.normals + s0 * TC_D * C;
+    if (full.uniforms) p.uniforms = full.uniforms + s0 * C;
+    tc_chain_ref_kernel<<<(unsigned)((C + 127) / 128), 128, 0, s>>>(ex->gram, (const float*)st->z, C, ex->cref, ex->crss);
+    if (a->rng_mode == AMCMC_RNG_EXTERNAL) diamonds_tc_adapt_kernel<true><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
+    else diamonds_tc_adapt_kernel<false><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
+    if ((rc = check_cuda(cudaGetLastError(), "diamonds_tc_adapt_kernel launch"))) return rc;
+  }
   tc_ldl_to_chol_kernel<<<ap.p.n_groups, TC_M, 0, s>>>(ap.ldl, (float*)st->scale, C);
   return check_cuda(cudaGetLastError(), "tc_ldl_to_chol_kernel launch");
 }

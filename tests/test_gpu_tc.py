@@ -316,3 +316,59 @@ def test_diamonds_tc_adaptive_spread_matches_block_kernel(diamonds_data):
         sd[impl] = raw["z"].double().permute(0, 2, 1).reshape(-1, d).std(0).cpu().numpy()
     r = sd[_lib.IMPL_TENSOR] / sd[_lib.IMPL_BLOCK]
     assert 0.85 < r.min() and r.max() < 1.18, r
+
+
+@pytest.mark.parametrize("segment", [1, 7, 16])
+def test_diamonds_tc_adaptive_segments(segment, diamonds_data, monkeypatch):
+    """Long launches are cut into segments with a re-centred GEMM reference point (256 steps by default).  Forcing
+    short segments must give the same chains (same Philox streams, same accept decisions up to the energy round-off)
+    and exactly the same sample bookkeeping: thinning, collect_start, accept record, iteration counter."""
+    C, d, T, thin, skip = 384, 26, 41, 3, 4
+    rng = np.random.default_rng(21)
+    q0 = _mode(diamonds_data)[None] + 0.004 * rng.normal(size=(C, d))
+    res = []
+    for seg in (None, segment):
+        if seg is None:
+            monkeypatch.delenv("AMCMC_TC_SEGMENT", raising=False)
+        else:
+            monkeypatch.setenv("AMCMC_TC_SEGMENT", str(seg))
+        s = _adaptive_sampler(C, q0, _lib.IMPL_TENSOR)
+        st = s.init(6, num_warmup=10, init_params=None, model_kwargs=diamonds_data)
+        b = am.ChainBatch.from_state(s.potential, st)
+        b.set_dense_scale(torch.eye(d) * 0.002)
+        raw = s.run_batch(b, T, thinning=thin, collect_start=skip, collect=("z", "potential_energy"), record_accept=True)
+        res.append((raw, b))
+    (r0, b0), (r1, b1) = res
+    S = (T - skip) // thin
+    assert r0["z"].shape == r1["z"].shape == (S, d, C) and r1["potential_energy"].shape == (S, C)
+    assert r1["accept"].shape == (T, C) and int(b1.i) == T
+    assert torch.isfinite(r1["z"]).all() and torch.isfinite(r1["potential_energy"]).all()
+    same = (r0["accept"] == r1["accept"]).all(dim=0)
+    assert same.float().mean() > 0.95
+    assert ((r0["z"][:, :, same] - r1["z"][:, :, same]).abs()).max() < 1e-4
+    assert ((b0.z[:, same] - b1.z[:, same]).abs()).max() < 1e-4
+    assert ((b0.lam[same] - b1.lam[same]).abs()).max() < 5e-2
+
+
+def test_diamonds_tc_adaptive_energies_from_far_start(diamonds_data):
+    """The reference's own start (q0 ~ U(-2,2)^26, factor = I): the batch is spread over |U| ~ 1e4-1e6 for tens of
+    thousands of steps.  Every chain has its own GEMM reference point, re-centred every 256 steps, so the stored
+    energies keep float32 accuracy there (a reference point shared by the batch measured 0.04 absolute)."""
+    C, d = 4096, 26
+    s = am.ARWMH(models.diamonds, num_chains=C)
+    st = s.init(11, num_warmup=0, init_params=None, model_kwargs=diamonds_data)
+    b = am.ChainBatch.from_state(s.potential, st)
+    raw = s.run_batch(b, 6000, thinning=500, collect=("z", "potential_energy"))
+    pot = o.make_potential("diamonds", **diamonds_data)
+    sel = np.arange(0, C, 16)
+    z = raw["z"].double().cpu().numpy()[:, :, sel]          # [S, d, 256]
+    pe = raw["potential_energy"].double().cpu().numpy()[:, sel]
+    exact = np.stack([pot(z[k].T) for k in range(z.shape[0])])
+    assert np.abs(exact).max() > 1e4                          # still far from the mode (U ~ -3.3e3 there)
+    rel = np.abs(pe - exact) / np.maximum(1.0, np.abs(exact))
+    assert rel.max() < 5e-6, rel.max()                        # a few tens of float32 ulps even at |U| ~ 1e6
+    mid = np.abs(exact) < 5e4
+    err = np.abs(pe - exact)[mid]
+    assert mid.any() and err.max() < 0.05 and np.median(err) < 2e-3, (err.max(), np.median(err))
+    assert np.median(exact[-1]) < np.median(exact[0])         # and the batch moves downhill
+    assert 0.1 < float(b.macc.mean()) < 0.4
