@@ -293,3 +293,35 @@ def test_odd_sizes_all_kernels():
         n = am.ARWMH(potential_fn=models.std_normal.bind(d=1, dtype=dt))
         out = n.sample_Pnx(0, torch.zeros(7, 1), am.ARWMHAdaptState(torch.zeros(1), torch.eye(1), torch.tensor(0.0)), n=3, n_samples=5)
         assert out.shape == (7, 5, 1) and torch.isfinite(out).all()
+
+
+def test_nan_guards_match_reference_semantics():
+    """The two silent guards of the reference are part of the numerical contract (SURVEY 8b 'Errors'):
+    a NaN / inf potential rejects the proposal (arwmh.py:171) and a NaN Cholesky update keeps the old factor (:191).
+    Draws that blow the proposal up (1e30, inf, nan) in a few chains: same decisions and same state as the NumPy
+    restatement of the reference step, the other chains untouched."""
+    C, T, d = 64, 12, 10
+    sampler = am.ARWMH(models.eight_schools, num_chains=C, dtype=torch.float64)
+    state = sampler.init(5, num_warmup=4, init_params=None)
+    ost = _oracle_state(state, np.float64)
+    rng = np.random.default_rng(17)
+    nrm = rng.normal(size=(T, C, d))
+    uni = rng.random(size=(T, C))
+    nrm[3, 0, :] = 1e30
+    nrm[2, 1, 4] = np.inf
+    nrm[4, 2, 0] = np.nan
+    nrm[6, 5, :] = -1e200
+    uni[:, 3] = 0.0
+    uni[:, 4] = 1.0 - 1e-12
+    coll, last = sampler.run(state, T, draws=(torch.from_numpy(nrm), torch.from_numpy(uni)), record_accept=True)
+    with np.errstate(all="ignore"):
+        olast, ocoll = o.arwmh_run(ost, o.make_potential("eight_schools"), T, draws=(nrm, uni), record_accept=True, num_warmup=4)
+    acc_g = coll["accept"].cpu().numpy().astype(bool)
+    np.testing.assert_array_equal(acc_g, ocoll["accepts"].astype(bool))
+    assert not acc_g[3, 0] and not acc_g[2, 1] and not acc_g[4, 2] and not acc_g[6, 5]
+    np.testing.assert_allclose(_np(torch.cat([v.reshape(C, -1) for v in last.z.values()], 1)), olast.z, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(_np(last.adapt_state.scale), olast.adapt_state.scale, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(_np(last.adapt_state.loc), olast.adapt_state.loc, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(_np(last.adapt_state.log_step_size), olast.adapt_state.log_step_size, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(_np(last.mean_accept_prob), olast.mean_accept_prob, rtol=1e-9, atol=1e-12)
+    assert np.isfinite(_np(last.adapt_state.scale)).all()

@@ -372,3 +372,38 @@ def test_diamonds_tc_adaptive_energies_from_far_start(diamonds_data):
     assert mid.any() and err.max() < 0.05 and np.median(err) < 2e-3, (err.max(), np.median(err))
     assert np.median(exact[-1]) < np.median(exact[0])         # and the batch moves downhill
     assert 0.1 < float(b.macc.mean()) < 0.4
+
+
+def test_diamonds_tc_adaptive_rejects_blown_up_proposals(diamonds_data):
+    """NaN / inf potential => reject (arwmh.py:171) on the tensor-core path: draws of 1e30 / inf / nan in a few chains
+    poison only those chains' rows of the GEMM; they reject, stay finite, and every other chain matches the exact
+    CUDA-core block kernel run with the same draws."""
+    C, d, T = 384, 26, 9
+    rng = np.random.default_rng(31)
+    q0 = _mode(diamonds_data)[None] + 0.004 * rng.normal(size=(C, d))
+    nrm = rng.normal(size=(T, C, d)).astype(np.float32)
+    uni = rng.random(size=(T, C)).astype(np.float32)
+    nrm[2, 0, :] = 1e30
+    nrm[3, 130, 5] = np.inf
+    nrm[4, 257, 0] = np.nan
+    nrm[5, 383, 25] = 1e30      # log sigma -> +inf
+    nrm[6, 7, 25] = -1e30       # log sigma -> -inf
+    bad = [(2, 0), (3, 130), (4, 257), (5, 383), (6, 7)]
+    res = {}
+    for impl in (_lib.IMPL_TENSOR, _lib.IMPL_BLOCK):
+        s = _adaptive_sampler(C, q0, impl)
+        st = s.init(1, num_warmup=0, init_params=None, model_kwargs=diamonds_data)
+        b = am.ChainBatch.from_state(s.potential, st)
+        b.set_dense_scale(torch.eye(d) * 0.002)
+        dr = s._draws_to_device_layout((torch.from_numpy(nrm), torch.from_numpy(uni)))
+        raw = s.run_batch(b, T, collect=("z", "potential_energy"), record_accept=True, draws=(dr[0], dr[1].to(dr[0].device)))
+        res[impl] = (raw["accept"].cpu().numpy().astype(bool), b.z.clone(), b.pe.clone(), b.scale.clone(), raw["z"].clone())
+    acc_t, acc_b = res[_lib.IMPL_TENSOR][0], res[_lib.IMPL_BLOCK][0]
+    for (t, c) in bad:
+        assert not acc_t[t, c] and not acc_b[t, c]
+    for k in range(1, 5):
+        assert torch.isfinite(res[_lib.IMPL_TENSOR][k]).all()
+    same = (acc_t == acc_b).all(axis=0)
+    assert same.mean() > 0.95
+    sel = torch.from_numpy(same).to(res[_lib.IMPL_TENSOR][1].device)
+    assert (res[_lib.IMPL_TENSOR][1][:, sel] - res[_lib.IMPL_BLOCK][1][:, sel]).abs().max() < 1e-4
