@@ -13,7 +13,9 @@ this path.  What this oracle *is* pinned against (tests/test_oracle.py):
     notebooks,
   * independent SciPy log-pdf formulas for every potential,
   * the algebraic contract of ``cholesky_update`` (L'L'^T = LL^T + c xx^T),
-  * Random123 known-answer vectors for Philox4x32-10.
+  * Random123 known-answer vectors for Philox4x32-10,
+  * (on the GPU side, tests/test_gpu_quality.py) the reference's recorded 100-seed quality table
+    rmse_means / wasserstein / mmd for ARWMH and ASSS, reproduced at the reference's own run lengths.
 
 Every function cites the reference file:line it restates (paths relative to
 /root/reference).  Third-party arithmetic that is *not* under /root/reference
