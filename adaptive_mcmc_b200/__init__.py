@@ -9,8 +9,9 @@ from .kernels import ARWMH, RAM, ASSS, ASSSState, ASSSAdaptState, ARWMHState, AR
 from .infer import MCMC
 from .utils.kernel_utils import ns_logscale, concat_trees, collect_states_logscale
 from . import diagnostics
+from .custom import custom_model
 
 __all__ = [
     "models", "ARWMH", "RAM", "ASSS", "ASSSState", "ASSSAdaptState", "ARWMHState", "ARWMHAdaptState", "ChainBatch", "init_to_uniform", "init_to_value",
-    "MCMC", "ns_logscale", "concat_trees", "collect_states_logscale", "diagnostics",
+    "custom_model", "MCMC", "ns_logscale", "concat_trees", "collect_states_logscale", "diagnostics",
 ]

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libamcmc.so")
 AMCMC_F32, AMCMC_F64 = 0, 1
 RNG_PHILOX, RNG_EXTERNAL = 0, 1
 KERNEL_ARWMH, KERNEL_RAM, KERNEL_ASSS = 0, 1, 2
-MODEL_STD_NORMAL, MODEL_EIGHT_SCHOOLS, MODEL_KIDIQ, MODEL_DIAMONDS, MODEL_GAUSSIAN = 0, 1, 2, 3, 4
+MODEL_STD_NORMAL, MODEL_EIGHT_SCHOOLS, MODEL_KIDIQ, MODEL_DIAMONDS, MODEL_GAUSSIAN, MODEL_CUSTOM = 0, 1, 2, 3, 4, 5
 IMPL_AUTO, IMPL_REGISTER, IMPL_BLOCK, IMPL_TENSOR = 0, 1, 2, 3
 
 
@@ -85,6 +85,7 @@ _lib = None
 # every symbol include/amcmc.h declares (tests check that the .so exports all of them)
 EXPORTED_SYMBOLS = (
     "amcmc_model_create",
+    "amcmc_model_create_custom",
     "amcmc_model_destroy",
     "amcmc_model_dim",
     "amcmc_model_dtype",
@@ -123,6 +124,10 @@ def lib():
     L.amcmc_model_create.argtypes = [
         C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int,
         C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int64),
+    ]
+    L.amcmc_model_create_custom.restype = C.c_int
+    L.amcmc_model_create_custom.argtypes = [
+        C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int64),
     ]
     L.amcmc_model_destroy.restype = C.c_int
     L.amcmc_model_destroy.argtypes = [C.c_void_p]

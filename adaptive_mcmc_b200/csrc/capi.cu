@@ -6,6 +6,7 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <dlfcn.h>
 #include "internal.h"
 
 namespace amcmc {
@@ -128,8 +129,58 @@ int amcmc_model_create(amcmc_model** out, int model_id, int dtype, int dim, int 
   return AMCMC_OK;
 }
 
+int amcmc_model_create_custom(amcmc_model** out, const char* plugin_path, int dtype, int n_arrays,
+                              const double* const* arrays, const int64_t* lens) {
+  if (!out) { set_error("amcmc_model_create_custom: out is NULL"); return AMCMC_ERR_ARG; }
+  *out = nullptr;
+  if (!plugin_path) { set_error("amcmc_model_create_custom: plugin_path is NULL"); return AMCMC_ERR_ARG; }
+  if (dtype != AMCMC_F32 && dtype != AMCMC_F64) { set_error("bad dtype %d", dtype); return AMCMC_ERR_ARG; }
+  if (n_arrays < 0 || n_arrays > 4 || (n_arrays > 0 && (!arrays || !lens))) {
+    set_error("custom model: 0..4 data arrays");
+    return AMCMC_ERR_ARG;
+  }
+  void* h = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) { set_error("custom model: dlopen(%s) failed: %s", plugin_path, dlerror()); return AMCMC_ERR_ARG; }
+  typedef int (*int_fn)(void);
+  int_fn f_dim = (int_fn)dlsym(h, "amcmc_plugin_dim");
+  int_fn f_abi = (int_fn)dlsym(h, "amcmc_plugin_abi");
+  void* f_run = dlsym(h, "amcmc_plugin_run");
+  void* f_init = dlsym(h, "amcmc_plugin_init");
+  void* f_pot = dlsym(h, "amcmc_plugin_potential");
+  if (!f_dim || !f_abi || !f_run || !f_init || !f_pot) {
+    set_error("custom model: %s does not export the amcmc_plugin_* entry points", plugin_path);
+    dlclose(h);
+    return AMCMC_ERR_ARG;
+  }
+  if (f_abi() != (int)sizeof(amcmc_model) * 1000 + AMCMC_VERSION) {
+    set_error("custom model: %s was built against another version of the library (rebuild the plugin)", plugin_path);
+    dlclose(h);
+    return AMCMC_ERR_ARG;
+  }
+  amcmc_model* m = (amcmc_model*)calloc(1, sizeof(amcmc_model));
+  m->model_id = AMCMC_MODEL_CUSTOM;
+  m->dtype = dtype;
+  m->dim = f_dim();
+  m->n_arrays = n_arrays;
+  m->plugin_handle = h;
+  m->plugin_run = (decltype(m->plugin_run))f_run;
+  m->plugin_init = (decltype(m->plugin_init))f_init;
+  m->plugin_potential = (decltype(m->plugin_potential))f_pot;
+  int rc = check_cuda(cudaGetDevice(&m->device), "cudaGetDevice");
+  for (int k = 0; k < n_arrays && !rc; ++k) {
+    if (lens[k] < 0 || (lens[k] > 0 && !arrays[k])) { set_error("custom model: bad array %d", k); rc = AMCMC_ERR_ARG; break; }
+    if (lens[k] > 0) rc = upload(arrays[k], lens[k], dtype, &m->d_arr[k]);
+    m->arr_len[k] = lens[k];
+  }
+  if (n_arrays > 0 && !rc) m->n_rows = lens[0];
+  if (rc) { amcmc_model_destroy(m); return rc; }
+  *out = m;
+  return AMCMC_OK;
+}
+
 int amcmc_model_destroy(amcmc_model* m) {
   if (!m) return AMCMC_OK;
+  if (m->plugin_handle) dlclose(m->plugin_handle);
   for (int k = 0; k < 4; ++k)
     if (m->d_arr[k]) cudaFree(m->d_arr[k]);
   if (m->scratch) cudaFree(m->scratch);
@@ -171,6 +222,7 @@ int amcmc_arwmh_init(const amcmc_model* m, amcmc_state* st, uint64_t seed, int64
     case AMCMC_MODEL_KIDIQ: return init_kidiq(m, st, seed, chain_offset, init_radius, use_given_z, s);
     case AMCMC_MODEL_DIAMONDS: return init_diamonds(m, st, seed, chain_offset, init_radius, use_given_z, s);
     case AMCMC_MODEL_GAUSSIAN: return init_gaussian(m, st, seed, chain_offset, init_radius, use_given_z, s);
+    case AMCMC_MODEL_CUSTOM: return m->plugin_init(m, st, seed, chain_offset, init_radius, use_given_z, s);
   }
   set_error("amcmc_arwmh_init: unsupported model %d", m->model_id);
   return AMCMC_ERR_UNSUPPORTED;
@@ -202,7 +254,7 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
   if (a->n_steps == 0) return AMCMC_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const bool small_family = m->model_id == AMCMC_MODEL_STD_NORMAL || m->model_id == AMCMC_MODEL_EIGHT_SCHOOLS ||
-                            m->model_id == AMCMC_MODEL_KIDIQ;
+                            m->model_id == AMCMC_MODEL_KIDIQ || m->model_id == AMCMC_MODEL_CUSTOM;
   if (a->kernel_kind != AMCMC_KERNEL_ARWMH && !(a->kernel_kind == AMCMC_KERNEL_RAM && m->model_id == AMCMC_MODEL_GAUSSIAN) &&
       !(a->kernel_kind == AMCMC_KERNEL_ASSS && small_family)) {
     set_error("amcmc_arwmh_run: kernel kind %d not available for model %d", a->kernel_kind, m->model_id);
@@ -220,6 +272,7 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
       break;
     }
     case AMCMC_MODEL_GAUSSIAN: rc = run_gaussian(m, st, a, s); break;
+    case AMCMC_MODEL_CUSTOM: rc = m->plugin_run(m, st, a, s); break;
     default:
       set_error("amcmc_arwmh_run: unsupported model %d", m->model_id);
       rc = AMCMC_ERR_UNSUPPORTED;
@@ -238,6 +291,7 @@ int amcmc_potential(const amcmc_model* m, int64_t n, const void* q, void* out, v
     case AMCMC_MODEL_KIDIQ: return potential_kidiq(m, n, q, out, s);
     case AMCMC_MODEL_DIAMONDS: return potential_diamonds_block(m, n, q, out, s);
     case AMCMC_MODEL_GAUSSIAN: return potential_gaussian(m, n, q, out, s);
+    case AMCMC_MODEL_CUSTOM: return m->plugin_potential(m, n, q, out, s);
   }
   set_error("amcmc_potential: unsupported model %d", m->model_id);
   return AMCMC_ERR_UNSUPPORTED;

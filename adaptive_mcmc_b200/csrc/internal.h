@@ -23,6 +23,11 @@ struct amcmc_model {
   cudaStream_t host_streams[2];  // [0] compute, [1] device->host sample copies (created lazily)
   cudaEvent_t host_events[4];    // [0..1] chunk computed, [2..3] chunk copied
   int host_streams_ready;
+  // custom families (AMCMC_MODEL_CUSTOM): entry points of the plugin library the potential was compiled into
+  void* plugin_handle;
+  int (*plugin_run)(const amcmc_model*, const amcmc_state*, const amcmc_run_args*, cudaStream_t);
+  int (*plugin_init)(const amcmc_model*, const amcmc_state*, uint64_t, int64_t, double, int, cudaStream_t);
+  int (*plugin_potential)(const amcmc_model*, int64_t, const void*, void*, cudaStream_t);
 };
 
 namespace amcmc {

@@ -47,7 +47,8 @@ enum amcmc_model_id {
   AMCMC_MODEL_EIGHT_SCHOOLS = 1, /* python/scripts/run_eight_schools_lr_decay.py:26-35 */
   AMCMC_MODEL_KIDIQ = 2,        /* python/scripts/run_kidiq_kidscore_lr_decay.py:29-41 */
   AMCMC_MODEL_DIAMONDS = 3,     /* python/scripts/run_diamonds_lr_decay.py:24-40 */
-  AMCMC_MODEL_GAUSSIAN = 4      /* BASELINE.json config 5: N(0, Sigma), precision Cholesky supplied */
+  AMCMC_MODEL_GAUSSIAN = 4,     /* BASELINE.json config 5: N(0, Sigma), precision Cholesky supplied */
+  AMCMC_MODEL_CUSTOM = 5        /* potential compiled from user CUDA source into a plugin (amcmc_model_create_custom) */
 };
 
 enum amcmc_rng_mode {
@@ -74,6 +75,13 @@ typedef struct amcmc_model amcmc_model; /* opaque: device copies of the model da
  */
 int amcmc_model_create(amcmc_model** out, int model_id, int dtype, int dim, int n_arrays,
                        const double* const* arrays, const int64_t* lens);
+/* The reference accepts ANY NumPyro model function (arwmh.py:43-78, 111-116: potential_fn traced by JAX).  The
+ * counterpart here: the potential is written as a CUDA device function, compiled together with the fused
+ * thread-per-chain kernels into a plugin library (adaptive_mcmc_b200/custom.py generates and builds it with nvcc),
+ * and bound to its data by this call.  `plugin_path`: the plugin .so; up to 4 HOST float64 arrays are copied to the
+ * device in `dtype` and handed to the potential as a0..a3 / n0..n3.  The model dimension comes from the plugin. */
+int amcmc_model_create_custom(amcmc_model** out, const char* plugin_path, int dtype, int n_arrays,
+                              const double* const* arrays, const int64_t* lens);
 int amcmc_model_destroy(amcmc_model* m);
 int amcmc_model_dim(const amcmc_model* m);
 int amcmc_model_dtype(const amcmc_model* m);
