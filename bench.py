@@ -327,7 +327,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
         extra = {}
         for name, fn in (("diamonds_tc", run_diamonds_tc), ("diamonds_tc_adaptive", run_diamonds_adaptive),
-                         ("gaussian_ram", run_gaussian_ram), ("asss_eight_schools", run_asss)):
+                         ("gaussian_ram", run_gaussian_ram), ("asss_eight_schools", run_asss),
+                         ("sample_Pnx_std_normal", run_sample_pnx)):
             try:
                 extra[name] = fn(args, world, rank, dev, max(3, K // 2), 2)
             except Exception as e:  # the headline line must survive a failure of a secondary workload
@@ -666,6 +667,41 @@ def run_asss(args, world, rank, dev, K, W):
                         "2,000 fused steps per launch, thinning 25 (the reference's ASSS thinning)",
             "metric": "chain-steps/sec", "value": world * Cn * T * K / (ms * 1e-3), "unit": "chain-steps/s", "ms_per_step": ms / K,
             "mean_shrink_iterations": float(b.macc.mean()), "gpu_launches": K}
+
+
+def run_sample_pnx(args, world, rank, dev, K, W):
+    """The reference's own many-chain benchmark (asumptions_check.ipynb cell 17, :L371-386): ARWMH.sample_Pnx on N(0,1),
+    d = 1, 100 start points x 10^5 samples x n = 5 steps with a frozen adaptation state -- 2.28 s wall on the author's
+    laptop (2.2e7 chain-steps/s).  Timed here as the whole API call (state set-up + one fused launch + result)."""
+    import torch
+    import torch.distributed as dist
+
+    import adaptive_mcmc_b200 as am
+
+    pot = am.models.std_normal.bind(d=1, device=dev)
+    s = am.ARWMH(potential_fn=pot, chain_offset=rank * 10_000_000)
+    x = torch.linspace(-3, 3, 100, device=dev)[:, None]
+    ast = am.ARWMHAdaptState(torch.zeros(1), torch.eye(1), torch.tensor(0.0))
+    for _ in range(max(W, 2)):
+        out = s.sample_Pnx(0, x, ast, n=5, n_samples=100_000)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        out = s.sample_Pnx(k, x, ast, n=5, n_samples=100_000)
+        m = float(out.mean())  # device -> host read of a result
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    te = torch.tensor([el], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    el = float(te.item())
+    return {"workload": "ARWMH.sample_Pnx, N(0,1) d=1, 100 points x 100,000 samples x n=5 frozen steps per call per GPU "
+                        "(python/jupyter/asumptions_check.ipynb cell 17)",
+            "metric": "chain-steps/sec", "value": world * 100 * 100_000 * 5 * K / el, "unit": "chain-steps/s", "ms_per_step": 1e3 * el / K,
+            "timing": "host wall clock around the whole API call", "reference_recorded": {"seconds_per_call": 2.28, "chain_steps_per_s": 2.2e7,
+            "hardware": "laptop CPU, JAX vmap (SURVEY section 6)"}, "last_mean": m, "gpu_launches": K * 3}
 
 
 def _traffic(key):
