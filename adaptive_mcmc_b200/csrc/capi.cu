@@ -256,7 +256,7 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
   const bool small_family = m->model_id == AMCMC_MODEL_STD_NORMAL || m->model_id == AMCMC_MODEL_EIGHT_SCHOOLS ||
                             m->model_id == AMCMC_MODEL_KIDIQ || m->model_id == AMCMC_MODEL_CUSTOM;
   if (a->kernel_kind != AMCMC_KERNEL_ARWMH && !(a->kernel_kind == AMCMC_KERNEL_RAM && m->model_id == AMCMC_MODEL_GAUSSIAN) &&
-      !(a->kernel_kind == AMCMC_KERNEL_ASSS && small_family)) {
+      !(a->kernel_kind == AMCMC_KERNEL_ASSS && (small_family || ((m->model_id == AMCMC_MODEL_DIAMONDS || m->model_id == AMCMC_MODEL_GAUSSIAN) && m->dim <= 32)))) {
     set_error("amcmc_arwmh_run: kernel kind %d not available for model %d", a->kernel_kind, m->model_id);
     return AMCMC_ERR_UNSUPPORTED;
   }
@@ -266,7 +266,8 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
     case AMCMC_MODEL_KIDIQ: rc = run_kidiq(m, st, a, s); break;
     case AMCMC_MODEL_DIAMONDS: {
       // many chains, fp32, per-chain adaptation: the likelihood goes to the tensor cores (impl 3 forces, impl 2 forbids)
-      const bool tc = a->adapt && diamonds_tc_available(m) && (a->impl == 3 || (a->impl == 0 && st->n_chains >= 4096));
+      const bool tc = a->adapt && a->kernel_kind == AMCMC_KERNEL_ARWMH && diamonds_tc_available(m) &&
+                      (a->impl == 3 || (a->impl == 0 && st->n_chains >= 4096));
       if (a->impl == 3 && !tc) { set_error("amcmc_arwmh_run: tensor-core path unavailable (needs fp32, K = 25, adapt = 1)"); rc = AMCMC_ERR_UNSUPPORTED; break; }
       rc = tc ? run_diamonds_tc_adapt(m, st, a, s) : run_diamonds_block(m, st, a, s);
       break;

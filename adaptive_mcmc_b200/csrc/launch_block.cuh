@@ -1,6 +1,7 @@
 // launch_block.cuh -- host-side launch helpers for the block-per-chain kernels.
 #pragma once
 #include "arwmh_block.cuh"
+#include "asss_block.cuh"
 #include "launch_small.cuh"
 
 namespace amcmc {
@@ -23,6 +24,19 @@ int launch_block_run(const BM& m, int d, const amcmc_state* st, const amcmc_run_
   const unsigned grid = (unsigned)st->n_chains;
   const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
   int rc = AMCMC_OK;
+  if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
+    if (!a->adapt) { set_error("ASSS: frozen mode is not available"); return AMCMC_ERR_UNSUPPORTED; }
+    if (ext) {
+      auto k = asss_block_kernel<BM, R, true>;
+      if ((rc = ensure_smem(k, smem))) return rc;
+      k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);
+    } else {
+      auto k = asss_block_kernel<BM, R, false>;
+      if ((rc = ensure_smem(k, smem))) return rc;
+      k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);
+    }
+    return check_cuda(cudaGetLastError(), "asss_block_kernel launch");
+  }
 #define AMCMC_LB(AD, EX)                                                              \
   do {                                                                                \
     auto k = arwmh_block_kernel<BM, R, AD, EX>;                                       \

@@ -4,7 +4,8 @@
 Same constructor kwargs (`model` xor `potential_fn`, `lr_decay`, `eps`, `init_strategy`), method names and
 state record names / field order as the reference; the step (stereographic projection, great-circle shrinkage
 with at most 50 trials, mean / Cholesky adaptation) runs in the thread-per-chain CUDA kernel
-``csrc/asss_small.cuh`` for the small-dimension models (eight_schools, kidiq, N(0, I_d)).
+``csrc/asss_small.cuh`` for the small-dimension models (eight_schools, kidiq, N(0, I_d), custom plugins) and
+``csrc/asss_block.cuh`` (one CTA per chain) for diamonds and the dense Gaussian family (d <= 32).
 Shared-draw parity mode: ``run(state, T, draws=(normals[T,C,d+1], uniforms[T,C,52]))`` with
 uniforms[..., 0] = u_t (asss.py:236), [..., 1] = theta_0 / 2pi (:61), [..., 2+k] = k-th shrinkage draw (:84).
 """

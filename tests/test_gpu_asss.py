@@ -83,3 +83,74 @@ def test_asss_posterior_matches_reference_table():
     assert float(ess.min()) / 32 > 6000  # reference: n_eff 9275-10281 of 10^4 kept draws
     it = float(mcmc.sampler.mean_shrink_iterations(mcmc.last_state).mean())
     assert 0.2 < it < 5.0, it
+
+
+# ---- block-per-chain ASSS: diamonds (the reference runs ASSS on diamonds too, run_diamonds_wasserstein.py 'sss') and
+# ---- the dense Gaussian family --------------------------------------------------------------------------------------
+def _diamonds_start(data, C, rng):
+    X, Y = np.asarray(data["X"], np.float64), np.asarray(data["Y"], np.float64)
+    Xc = np.column_stack([np.ones(len(Y)), X[:, 1:] - X[:, 1:].mean(0)])
+    mode = np.concatenate([np.linalg.lstsq(Xc, Y, rcond=None)[0], [np.log(0.123)]])
+    return mode[None] + 0.01 * rng.normal(size=(C, 26))
+
+
+@pytest.mark.parametrize("prec,T,tol", [("f64", 25, 1e-5), ("f32", 12, 2e-3)])
+def test_asss_diamonds_block_shared_draws(prec, T, tol):
+    tdt, ndt = (torch.float64, np.float64) if prec == "f64" else (torch.float32, np.float32)
+    data = models.synthetic_diamonds(n=5000, k=25, seed=0)
+    C, d = 48, 26
+    rng = np.random.default_rng(3)
+    q0 = _diamonds_start(data, C, rng)
+    s = am.ASSS(models.diamonds, num_chains=C, dtype=tdt, init_strategy=am.init_to_value(torch.from_numpy(q0)))
+    st = s.init(1, num_warmup=5, init_params=None, model_kwargs=data)
+    b = s._batch_from_state(st)
+    b.set_dense_scale(torch.eye(d, dtype=tdt) * 0.01)     # scale = I leaves the sphere far too wide for this posterior
+    st = s._state_from_batch(b)
+    pot = o.make_potential("diamonds", **data)
+    z0 = b.z.t().cpu().numpy().astype(ndt)
+    ost = oa.asss_init(lambda q: pot(q.astype(np.float64)).astype(ndt), z0)
+    ost = ost._replace(adapt_state=ost.adapt_state._replace(scale=np.broadcast_to(np.eye(d, dtype=ndt) * ndt(0.01), (C, d, d)).copy()))
+    nrm = rng.normal(size=(T, C, d + 1)).astype(ndt)
+    uni = rng.random(size=(T, C, 52)).astype(ndt)
+    coll, last = s.run(st, T, draws=(torch.from_numpy(nrm), torch.from_numpy(uni)))
+    olast, ocoll = oa.asss_run(ost, lambda q: pot(q.astype(np.float64)).astype(ndt), T, draws=(nrm, uni), num_warmup=5)
+    zg = np.concatenate([_np(v).reshape(T, C, -1) for v in coll["z"].values()], axis=-1)
+    err = (np.abs(zg - ocoll["z"]) / (1 + np.abs(ocoll["z"]))).max(axis=(0, 2))
+    if prec == "f64":
+        assert err.max() < tol, err.max()
+    else:
+        assert np.quantile(err, 0.8) < tol, np.quantile(err, [0.5, 0.8, 1.0])
+    good = err < 10 * tol
+    np.testing.assert_allclose(_np(last.adapt_state.scale)[good], olast.adapt_state.scale[good], rtol=50 * tol, atol=50 * tol * 0.01)
+    np.testing.assert_allclose(_np(last.adapt_state.loc)[good], olast.adapt_state.loc[good], rtol=20 * tol, atol=20 * tol)
+    np.testing.assert_allclose(_np(last.as_change)[good], olast.as_change[good], rtol=50 * tol, atol=1e-6)
+    assert int(last.i) == T and (zg[-1] != z0).any()
+
+
+def test_asss_gaussian_block_philox_and_moments():
+    """Dense Gaussian d = 12 on the block kernel: the Philox stream follows the oracle's (same words; the device normals
+    use SFU log / sin / cos, so single-precision agreement), and a longer run recovers the target covariance."""
+    d, C = 12, 64
+    P = models.ar1_precision_chol(d, 0.6)
+    s = am.ASSS(models.gaussian, num_chains=C, dtype=torch.float64, chain_offset=5)
+    st = s.init(4, num_warmup=0, init_params=None, model_kwargs=dict(prec_chol=P))
+    Pn = np.asarray(P, np.float64)
+    pot = lambda q: 0.5 * ((q @ np.tril(Pn)) ** 2).sum(1)
+    ost = oa.asss_init(pot, co.init_uniform(4, C, d, dt=np.float64, chain_offset=5))
+    np.testing.assert_allclose(_np(st.potential_energy), ost.potential_energy, rtol=1e-10)
+    coll, last = s.run(st, 30, thinning=3)
+    olast, ocoll = oa.asss_run(ost, pot, 30, seed=4, chain_offset=5, thinning=3)
+    err = (np.abs(_np(coll["z"]["x"]) - ocoll["z"]) / (1 + np.abs(ocoll["z"]))).max(axis=(0, 2))
+    assert np.quantile(err, 0.9) < 1e-3, np.quantile(err, [0.5, 0.9, 1.0])  # device normals use SFU log/sin/cos
+    good = err < 1e-3
+    np.testing.assert_allclose(_np(last.adapt_state.scale)[good], olast.adapt_state.scale[good], rtol=2e-2, atol=2e-3)
+    # moments
+    # (while the Robbins-Monro weights are still large the sample is over-dispersed -- 1.36 on the diagonal after
+    # 2k + 4k steps, in fp64 as in fp32 -- so the moments are checked on a run of the reference's length)
+    s2 = am.ASSS(models.gaussian, num_chains=512, dtype=torch.float32)
+    st2 = s2.init(9, num_warmup=20000, init_params=None, model_kwargs=dict(prec_chol=P))
+    coll2, _ = s2.run(st2, 60000, thinning=20, collect_start=20000)
+    x = coll2["z"]["x"].double().reshape(-1, d).cpu().numpy()
+    cov = np.linalg.inv(np.tril(Pn) @ np.tril(Pn).T)
+    emp = np.cov(x.T)
+    assert np.abs(emp - cov).max() < 0.04, np.abs(emp - cov).max()
