@@ -142,3 +142,48 @@ def test_custom_model_asss_matches_oracle():
     olast, _ = oa.asss_run(ost, pot, T, draws=(nrm, uni))
     np.testing.assert_allclose(last.z["beta"].cpu().numpy(), olast.z, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(last.adapt_state.scale.cpu().numpy(), olast.adapt_state.scale, rtol=1e-6, atol=1e-8)
+
+
+LOGISTIC_ROW = '''
+    const R eta = q[0] + q[1] * a0[2 * i] + q[2] * a0[2 * i + 1];
+    const R sp = eta > (R)0 ? eta + Num<R>::log1p(Num<R>::exp(-eta)) : Num<R>::log1p(Num<R>::exp(eta));
+    return sp - a1[i] * eta;'''
+LOGISTIC_PRIOR = "    return (R)0.02 * (q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["arwmh", "asss"])
+def test_custom_block_model_matches_oracle(kind):
+    """A data-heavy custom model (logistic regression, 20,000 rows) on the CTA-per-chain kernels: the rows of the
+    likelihood are spread over the chain's CTA like the diamonds likelihood."""
+    x, y = _logistic_data(20000, seed=2)
+    fam = am.custom_model("t_logistic_rows", [("beta", (3,))], arrays=["x", "y"], rows="y", row_term=LOGISTIC_ROW, prior=LOGISTIC_PRIOR)
+    pot = _logistic_potential(x, y)
+    C, d = 96, 3
+    rng = np.random.default_rng(8)
+    q0 = np.array([0.5, 1.2, -0.7])[None] + 0.05 * rng.normal(size=(C, d))
+    cls = am.ARWMH if kind == "arwmh" else am.ASSS
+    s = cls(fam, num_chains=C, dtype=torch.float64, init_strategy=am.init_to_value(torch.from_numpy(q0)))
+    st = s.init(0, num_warmup=5, init_params=None, model_kwargs=dict(x=x, y=y))
+    np.testing.assert_allclose(st.potential_energy.cpu().numpy(), pot(q0), rtol=1e-11)
+    b = s._batch_from_state(st)
+    b.set_dense_scale(torch.eye(d, dtype=torch.float64) * 0.02)
+    st = s._state_from_batch(b)
+    T = 30
+    if kind == "arwmh":
+        nrm, uni = rng.normal(size=(T, C, d)), rng.random(size=(T, C))
+        coll, last = s.run(st, T, draws=(torch.from_numpy(nrm), torch.from_numpy(uni)), record_accept=True)
+        ost = o.arwmh_init(pot, q0)
+        ost = ost._replace(adapt_state=ost.adapt_state._replace(scale=np.broadcast_to(np.eye(d) * 0.02, (C, d, d)).copy()))
+        olast, ocoll = o.arwmh_run(ost, pot, T, draws=(nrm, uni), record_accept=True, num_warmup=5)
+        np.testing.assert_array_equal(coll["accept"].cpu().numpy().astype(bool), ocoll["accepts"].astype(bool))
+        assert 0.05 < ocoll["accepts"].mean() < 0.95
+    else:
+        nrm, uni = rng.normal(size=(T, C, d + 1)), rng.random(size=(T, C, 52))
+        coll, last = s.run(st, T, draws=(torch.from_numpy(nrm), torch.from_numpy(uni)))
+        ost = oa.asss_init(pot, q0)
+        ost = ost._replace(adapt_state=ost.adapt_state._replace(scale=np.broadcast_to(np.eye(d) * 0.02, (C, d, d)).copy()))
+        olast, _ = oa.asss_run(ost, pot, T, draws=(nrm, uni), num_warmup=5)
+    np.testing.assert_allclose(last.z["beta"].cpu().numpy(), olast.z, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(last.adapt_state.scale.cpu().numpy(), olast.adapt_state.scale, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(last.potential_energy.cpu().numpy(), olast.potential_energy, rtol=1e-9)
