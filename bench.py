@@ -222,18 +222,26 @@ def run_ours(args):
         raw = one_step()  # holding the previous result, like the timed loop: both 577 MB sample buffers get allocated here
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    n_ess = min(Cn, 4096)
+    # ESS sample of every timed step, allocated up front: no allocator call (cudaMalloc) between the timed steps
+    kept_buf = torch.empty(K, T // args.thinning, d, n_ess, dtype=tdt, device=dev)
     kept = []
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    n_ess = min(Cn, 4096)
+    # two more untimed steps after the last allocation: a sample buffer that the caching allocator hands out for the
+    # first time costs its kernel ~8 ms of first-touch (31 ms instead of 22.6 ms), and which step gets it is an accident
+    for _ in range(2):
+        raw = one_step()
+    torch.cuda.synchronize()
     mark0 = clocks.mark()
     for k in range(K):
         flush.fill_(k & 0xFF)  # L2 flush between timed iterations (not timed)
         ev[k][0].record()
         raw = one_step()
         ev[k][1].record()
-        kept.append(raw["z"][:, :, :n_ess].clone())
+        kept_buf[k].copy_(raw["z"][:, :, :n_ess])
+        kept.append(kept_buf[k])
     torch.cuda.synchronize()
     mark1 = clocks.mark()
     if world > 1:
