@@ -36,20 +36,21 @@ def concat_trees(trees):
     return _leaves_cat(list(trees))
 
 
-def _snapshot(batch: ChainBatch):
-    """Full ARWMHState at the current iteration with a leading sample axis of length 1."""
-    pot = batch.potential
-    z = OrderedDict((k, v.clone().unsqueeze(0)) for k, v in pot.unravel(batch.z.t()).items())
-    adapt = ARWMHAdaptState(batch.loc.t().clone().unsqueeze(0), batch.dense_scale().unsqueeze(0), batch.lam.clone().unsqueeze(0))
-    return ARWMHState(
-        torch.tensor([batch.i]),
-        z,
-        batch.pe.clone().unsqueeze(0),
-        batch.macc.clone().unsqueeze(0),
-        adapt,
-        batch.asc.clone().unsqueeze(0),
-        torch.tensor([[batch.seed, batch.chain_offset]], dtype=torch.int64),
-    )
+def _snapshot(sampler, batch: ChainBatch):
+    """Full sampler state (ARWMHState / ASSSState / ...) at the current iteration, every leaf cloned and given a leading
+    sample axis of length 1."""
+    st = sampler._state_from_batch(batch)
+
+    def lift(v):
+        if isinstance(v, torch.Tensor):
+            return v.clone().unsqueeze(0) if v.dim() > 0 else v.clone().reshape(1)
+        if isinstance(v, dict):
+            return type(v)((k, lift(x)) for k, x in v.items())
+        if isinstance(v, tuple) and hasattr(v, "_fields"):
+            return type(v)(*[lift(x) for x in v])
+        return torch.tensor([v])
+
+    return lift(st)
 
 
 def collect_states_logscale(rng_key, sampler, model_data: dict, n_pow=6):
@@ -67,5 +68,5 @@ def collect_states_logscale(rng_key, sampler, model_data: dict, n_pow=6):
         thinning = 10 ** (max(0, p - 2))
         for _ in range((upper_idx - lower_idx) // thinning):
             sampler.run_batch(batch, thinning, collect=())
-            collections.append(_snapshot(batch))
+            collections.append(_snapshot(sampler, batch))
     return concat_trees(collections)
