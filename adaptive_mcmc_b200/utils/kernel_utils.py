@@ -50,7 +50,11 @@ def _snapshot(sampler, batch: ChainBatch):
             return type(v)(*[lift(x) for x in v])
         return torch.tensor([v])
 
-    return lift(st)
+    out = lift(st)
+    if hasattr(out, "rng_key"):  # one key per chain: (seed, global chain id) identifies the chain's Philox stream
+        ids = torch.arange(batch.C, dtype=torch.int64) + int(batch.chain_offset)
+        out = out._replace(rng_key=torch.stack([torch.full_like(ids, int(batch.seed) & 0x7FFFFFFFFFFFFFFF), ids], dim=1).unsqueeze(0))
+    return out
 
 
 def collect_states_logscale(rng_key, sampler, model_data: dict, n_pow=6):

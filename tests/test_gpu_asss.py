@@ -154,3 +154,36 @@ def test_asss_gaussian_block_philox_and_moments():
     cov = np.linalg.inv(np.tril(Pn) @ np.tril(Pn).T)
     emp = np.cov(x.T)
     assert np.abs(emp - cov).max() < 0.04, np.abs(emp - cov).max()
+
+
+def test_asss_logscale_collection_and_reference_pickle(tmp_path):
+    """collect_states_logscale (python/utils/kernel_utils.py:20-38) with the slice sampler, written in the reference's
+    pickle layout: `kernels.asss.ASSSState` records with [sample, ...] NumPy leaves."""
+    import pickle
+    import sys
+    import types
+    from collections import namedtuple
+
+    from adaptive_mcmc_b200.utils import io as amio
+
+    s = am.ASSS(models.eight_schools, lr_decay=0.5, num_chains=6)
+    states = am.collect_states_logscale(3, s, dict(y=models.eight_schools.Y, sigma=models.eight_schools.SIGMA), n_pow=3)
+    grid = am.ns_logscale(3)
+    assert type(states).__name__ == "ASSSState" and states.as_change.shape == (len(grid), 6)
+    np.testing.assert_array_equal(_np(states.i).ravel(), grid.numpy())
+    assert states.adapt_state.scale.shape == (len(grid), 6, 10, 10) and states.z["theta_base"].shape == (len(grid), 6, 8)
+    path = tmp_path / "run4.pkl"
+    amio.save_states(states, str(path), chain=4)
+    # load it the way the reference environment would: with ITS record classes importable as kernels.asss.*
+    mod_k, mod_a = types.ModuleType("kernels"), types.ModuleType("kernels.asss")
+    mod_a.ASSSState = namedtuple("ASSSState", ["i", "z", "potential_energy", "adapt_state", "as_change", "rng_key"])
+    mod_a.ASSSAdaptState = namedtuple("ASSSAdaptState", ["loc", "scale"])
+    mod_a.ASSSState.__module__ = mod_a.ASSSAdaptState.__module__ = "kernels.asss"
+    sys.modules["kernels"], sys.modules["kernels.asss"] = mod_k, mod_a
+    try:
+        got = pickle.load(open(path, "rb"))
+    finally:
+        sys.modules.pop("kernels.asss"), sys.modules.pop("kernels")
+    assert isinstance(got, mod_a.ASSSState) and isinstance(got.adapt_state, mod_a.ASSSAdaptState)
+    np.testing.assert_allclose(got.potential_energy, _np(states.potential_energy)[:, 4])
+    assert got.adapt_state.scale.shape == (len(grid), 10, 10) and got.z["mu"].shape == (len(grid),)
