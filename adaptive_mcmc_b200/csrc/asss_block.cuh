@@ -15,7 +15,7 @@ namespace amcmc {
 
 #ifdef __CUDACC__
 
-template <class BM, typename R, bool EXTERNAL>
+template <class BM, typename R, bool EXTERNAL, bool ADAPT>
 __global__ void __launch_bounds__(kBlockThreads)
 asss_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const int d) {
   constexpr int NT = kBlockThreads;
@@ -183,13 +183,13 @@ asss_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const i
       const R xn = sm.xp[k];
       const R dl = xn - sm.mu[k];
       sm.x[k] = xn;
-      sm.mu[k] = fma(gamma, dl, sm.mu[k]);
+      if (ADAPT) sm.mu[k] = fma(gamma, dl, sm.mu[k]);
       sm.w[k] = dl;
       ok_local &= (Num<R>::abs(dl) < Num<R>::kBig) && (sm.Dg[k] > (R)0);
     }
     U = Un;
-    const int ok = __syncthreads_and(ok_local) && !n_is_one;
-    if (tid < 32) {
+    const int ok = __syncthreads_and(ok_local) && !n_is_one && ADAPT;  // frozen (sample_Pnx): no update at all
+    if (ADAPT && tid < 32) {
       R dn = 0;
       if (last) dn = warp_sum(tid < d ? sm.w[tid] * sm.w[tid] : (R)0);
       R ss = 0;
@@ -209,8 +209,10 @@ asss_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const i
   }
   // ---- store
   __syncthreads();
+  for (int k = tid; k < d; k += NT) st.z[k * C + c] = sm.x[k];
+  if (tid == 0) st.pe[c] = U;
+  if (!ADAPT) return;
   for (int k = tid; k < d; k += NT) {
-    st.z[k * C + c] = sm.x[k];
     st.loc[k * C + c] = sm.mu[k];
     const R sd = ::sqrt(sm.Dg[k]);
     sm.y[k] = sd;
@@ -224,7 +226,7 @@ asss_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const i
     const int j = e2 - i * (i - 1) / 2;
     st.scale[(int64_t)tri_full(i, j) * C + c] = sm.Lt[cm_idx(i, j, d)] * sm.y[j];
   }
-  if (tid == 0) { st.pe[c] = U; st.macc[c] = macc; st.asc[c] = asc; }
+  if (tid == 0) { st.macc[c] = macc; st.asc[c] = asc; }
 }
 
 #endif  // __CUDACC__

@@ -54,7 +54,7 @@ AMCMC_HD R asss_transformed(const ChainRegs<R, Model::D>& s, const Model& m, con
 }
 
 // vn: D+1 normals; u_t, u_th: uniforms; next_u(k): k-th shrinkage uniform (lazily evaluated)
-template <class Model, typename R, class NextU>
+template <class Model, typename R, bool ADAPT, class NextU>
 AMCMC_HD int asss_step(ChainRegs<R, Model::D>& s, const Model& m, const R (&vn)[Model::D + 1], R u_t, R u_th,
                        NextU next_u, R nf, bool n_is_one, R lr_decay, R eps, bool want_asc) {
   constexpr int D = Model::D;
@@ -123,6 +123,12 @@ AMCMC_HD int asss_step(ChainRegs<R, Model::D>& s, const Model& m, const R (&vn)[
     asss_transformed<Model, R>(s, m, cs, eps_dsq, zc, zl, xn, Un, om);
   }
   if (Num<R>::isnan(Un)) Un = Num<R>::inf();  // :244
+  if (!ADAPT) {  // sample_Pnx (:279-315): the step is taken with the given adapt_state, no update
+#pragma unroll
+    for (int k = 0; k < D; ++k) s.x[k] = xn[k];
+    s.U = Un;
+    return iter;
+  }
   // ---- adaptation (:246-267)
   const R gamma = n_is_one ? (R)1 : Num<R>::pow_neg(nf, lr_decay);
   R w[D], dn = 0;
@@ -173,7 +179,7 @@ AMCMC_HD void asss_philox_head(const Philox& g, uint64_t step, R (&vn)[D + 1], R
   u_th = (R)word_to_uniform(w[2 * NPAIR + 1]);
 }
 
-template <class Model, typename R, bool EXTERNAL>
+template <class Model, typename R, bool EXTERNAL, bool ADAPT>
 AMCMC_HD void asss_chain_run(const Model& m, const StateView<R>& st, const RunView<R>& a, int64_t c) {
   constexpr int D = Model::D;
   const int64_t C = st.C;
@@ -203,7 +209,7 @@ AMCMC_HD void asss_chain_run(const Model& m, const StateView<R>& st, const RunVi
     };
     const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
     const bool last = (t == a.n_steps - 1);
-    asss_step<Model, R>(s, m, vn, u_t, u_th, next_u, (R)n, n == 1, a.lr_decay, a.eps, last);
+    asss_step<Model, R, ADAPT>(s, m, vn, u_t, u_th, next_u, (R)n, n == 1, a.lr_decay, a.eps, last);
     if (--until_collect == 0) {
       until_collect = a.thinning;
       if (a.out_z) {
@@ -214,17 +220,17 @@ AMCMC_HD void asss_chain_run(const Model& m, const StateView<R>& st, const RunVi
       ++sidx;
     }
   }
-  store_chain<R, D, true>(s, st, c);
+  store_chain<R, D, ADAPT>(s, st, c);
 }
 
 #ifdef __CUDACC__
-template <class Model, typename R, bool EXTERNAL>
+template <class Model, typename R, bool EXTERNAL, bool ADAPT>
 // 7 resident CTAs of 64 threads per SM (128 registers): 65,536 chains fit in ONE wave, as for arwmh_small_kernel
 __global__ void __launch_bounds__(64, (sizeof(R) == 4 ? 7 : 1))
 asss_small_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st.C) return;
-  asss_chain_run<Model, R, EXTERNAL>(m, st, a, c);
+  asss_chain_run<Model, R, EXTERNAL, ADAPT>(m, st, a, c);
 }
 #endif
 

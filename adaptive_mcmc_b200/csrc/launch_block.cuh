@@ -25,16 +25,15 @@ int launch_block_run(const BM& m, int d, const amcmc_state* st, const amcmc_run_
   const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
   int rc = AMCMC_OK;
   if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
-    if (!a->adapt) { set_error("ASSS: frozen mode is not available"); return AMCMC_ERR_UNSUPPORTED; }
-    if (ext) {
-      auto k = asss_block_kernel<BM, R, true>;
-      if ((rc = ensure_smem(k, smem))) return rc;
-      k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);
-    } else {
-      auto k = asss_block_kernel<BM, R, false>;
-      if ((rc = ensure_smem(k, smem))) return rc;
-      k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);
-    }
+#define AMCMC_LA(EX, AD)                                                              \
+  do {                                                                                \
+    auto k = asss_block_kernel<BM, R, EX, AD>;                                        \
+    if ((rc = ensure_smem(k, smem))) return rc;                                       \
+    k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);                                \
+  } while (0)
+    if (a->adapt) { if (ext) AMCMC_LA(true, true); else AMCMC_LA(false, true); }
+    else          { if (ext) AMCMC_LA(true, false); else AMCMC_LA(false, false); }  // frozen: ASSS.sample_Pnx
+#undef AMCMC_LA
     return check_cuda(cudaGetLastError(), "asss_block_kernel launch");
   }
 #define AMCMC_LB(AD, EX)                                                              \

@@ -49,9 +49,13 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
   const unsigned grid = (unsigned)((st->n_chains + block - 1) / block);
   const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
   if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
-    if (!a->adapt) { set_error("ASSS: frozen mode is not available"); return AMCMC_ERR_UNSUPPORTED; }
-    if (ext) asss_small_kernel<Model, R, true><<<grid, block, 0, s>>>(m, sv, rv);
-    else     asss_small_kernel<Model, R, false><<<grid, block, 0, s>>>(m, sv, rv);
+    if (a->adapt) {
+      if (ext) asss_small_kernel<Model, R, true, true><<<grid, block, 0, s>>>(m, sv, rv);
+      else     asss_small_kernel<Model, R, false, true><<<grid, block, 0, s>>>(m, sv, rv);
+    } else {  // frozen adapt_state: ASSS.sample_Pnx (asss.py:279-315)
+      if (ext) asss_small_kernel<Model, R, true, false><<<grid, block, 0, s>>>(m, sv, rv);
+      else     asss_small_kernel<Model, R, false, false><<<grid, block, 0, s>>>(m, sv, rv);
+    }
     return check_cuda(cudaGetLastError(), "asss_small_kernel launch");
   }
   if (a->adapt) {

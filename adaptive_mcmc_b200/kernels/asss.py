@@ -84,7 +84,11 @@ class ASSS(ARWMH):
         return self._batch_from_state(state, copy=False).macc
 
     def get_diagnostics_str(self, state):
-        return ""
+        """asss.py:276-277 (potential energy averaged over the chains)."""
+        return f"Iteration: {int(state.i)}, Potential Energy: {float(torch.as_tensor(state.potential_energy).float().mean()):.2f}"
 
-    def sample_Pnx(self, *a, **k):
-        raise NotImplementedError("sample_Pnx (frozen kernel) is available for ARWMH only")
+    def sample_Pnx(self, rng_key, x, adapt_state, n=1, n_samples=1000, jit_inner=True):
+        """asss.py:279-315 -- P^n(x, .) of the slice sampler with the adaptation state (loc, scale) FROZEN: for each
+        start point `n_samples` independent chains of `n` steps; returns the final positions [n_points, n_samples, ...]."""
+        loc, scale = adapt_state[0], adapt_state[1]
+        return super().sample_Pnx(rng_key, x, ARWMHAdaptState(loc, scale, torch.tensor(0.0)), n=n, n_samples=n_samples)

@@ -44,7 +44,7 @@ def _inverse(z, loc, S):
     return np.einsum("cij,cj->ci", S, xb) + loc
 
 
-def asss_step(state, potential, normals, uniforms, num_warmup=0, lr_decay=2.0 / 3.0, eps=1e-6):
+def asss_step(state, potential, normals, uniforms, num_warmup=0, lr_decay=2.0 / 3.0, eps=1e-6, adapt=True):
     """One ASSS.sample (asss.py:192-269) for C chains with supplied draws.
     Returns (new_state, n_shrink_iterations[C])."""
     i = state.i
@@ -99,6 +99,8 @@ def asss_step(state, potential, normals, uniforms, num_warmup=0, lr_decay=2.0 / 
         bad = np.isnan(chol).any(axis=(1, 2))
         scale_new = np.where(bad[:, None, None], scale, chol)
         as_change = np.linalg.norm(loc_new - loc, axis=1) + np.sqrt(np.sum((scale_new - scale) ** 2, axis=(1, 2)))
+    if not adapt:  # sample_Pnx (asss.py:279-315): every step is taken with the GIVEN adapt_state, its update is dropped
+        return ASSSState(itr, x_new, pe_new, state.adapt_state, state.as_change, state.rng_key), it
     new = ASSSState(itr, x_new, pe_new, ASSSAdaptState(loc_new.astype(dt), scale_new.astype(dt)), as_change.astype(dt),
                     state.rng_key)
     return new, it

@@ -187,3 +187,47 @@ def test_asss_logscale_collection_and_reference_pickle(tmp_path):
     assert isinstance(got, mod_a.ASSSState) and isinstance(got.adapt_state, mod_a.ASSSAdaptState)
     np.testing.assert_allclose(got.potential_energy, _np(states.potential_energy)[:, 4])
     assert got.adapt_state.scale.shape == (len(grid), 10, 10) and got.z["mu"].shape == (len(grid),)
+
+
+def test_asss_sample_Pnx_frozen_kernel():
+    """ASSS.sample_Pnx (asss.py:279-315): the slice sampler with a FROZEN (loc, scale).  (i) exact N(0, I_2) draws pushed
+    through P^n stay N(0, I_2) (asumptions_check.ipynb cells 32-33 run the ASSS twin of the ARWMH check); (ii) the frozen
+    step equals the oracle's on shared draws and leaves the adaptation state untouched, on both kernel families."""
+    from scipy import stats
+
+    pot = models.std_normal.bind(d=2, dtype=torch.float32)
+    s = am.ASSS(potential_fn=pot)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(100000, 2, generator=g)
+    adapt = am.ASSSAdaptState(torch.tensor([0.3, -0.2]), torch.tensor([[1.2, 0.0], [0.4, 0.8]]))
+    out = s.sample_Pnx(5, x, adapt, n=3, n_samples=2)
+    assert out.shape == (100000, 2, 2)
+    y = out.reshape(-1, 2).double().cpu().numpy()
+    assert np.abs(y.mean(0)).max() < 0.01 and np.abs(y.std(0) - 1).max() < 0.01 and abs(np.corrcoef(y.T)[0, 1]) < 0.01
+    assert stats.kstest(y[::4, 0], "norm").pvalue > 1e-3 and stats.kstest(y[::4, 1], "norm").pvalue > 1e-3
+    assert "Potential Energy" in s.get_diagnostics_str(s.init(0, 0, init_params=torch.zeros(4, 2)))
+    # (ii) shared draws, frozen, register kernel (eight_schools) and block kernel (Gaussian d = 12)
+    rng = np.random.default_rng(2)
+    for family, kw, name, d in ((models.eight_schools, {}, "eight_schools", 10),
+                                (models.gaussian, dict(prec_chol=models.ar1_precision_chol(12, 0.5)), None, 12)):
+        C, T = 64, 15
+        smp = am.ASSS(family, num_chains=C, dtype=torch.float64)
+        st = smp.init(3, num_warmup=0, init_params=None, model_kwargs=kw)
+        b = smp._batch_from_state(st)
+        scale0 = torch.tril(torch.from_numpy(rng.normal(size=(d, d)) * 0.1 + np.eye(d)))
+        b.set_dense_scale(scale0)
+        loc0, sc0 = b.loc.clone(), b.scale.clone()
+        nrm, uni = rng.normal(size=(T, C, d + 1)), rng.random(size=(T, C, 52))
+        dr = smp._draws_to_device_layout((torch.from_numpy(nrm), torch.from_numpy(uni)))
+        z0 = b.z.t().cpu().numpy().copy()
+        smp.run_batch(b, T, collect=(), draws=dr, adapt=False)
+        assert torch.equal(b.loc, loc0) and torch.equal(b.scale, sc0)
+        if name:
+            potf = o.make_potential(name)
+        else:
+            Pn = np.tril(np.asarray(kw["prec_chol"], np.float64))
+            potf = lambda q: 0.5 * ((q @ Pn) ** 2).sum(1)
+        ost = oa.asss_init(potf, z0)
+        ost = ost._replace(adapt_state=oa.ASSSAdaptState(z0.copy(), np.broadcast_to(scale0.numpy(), (C, d, d)).copy()))
+        olast, _ = oa.asss_run(ost, potf, T, draws=(nrm, uni), adapt=False)
+        np.testing.assert_allclose(b.z.t().cpu().numpy(), olast.z, rtol=1e-6, atol=1e-8)
