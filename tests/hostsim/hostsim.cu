@@ -52,8 +52,8 @@ static void run_es_asss(const double* y, const double* sigma, double cst, int64_
   RunView<R> a{i0, n_steps, thinning, collect_start, num_warmup, (R)lr, (R)target, (R)eps, seed, chain_offset,
                normals, uniforms, out_z, out_pe, out_acc};
   for (int64_t c = 0; c < C; ++c) {
-    if (normals) asss_chain_run<EightSchoolsModel<R>, R, true>(m, st, a, c);
-    else asss_chain_run<EightSchoolsModel<R>, R, false>(m, st, a, c);
+    if (normals) asss_chain_run<EightSchoolsModel<R>, R, true, true>(m, st, a, c);
+    else asss_chain_run<EightSchoolsModel<R>, R, false, true>(m, st, a, c);
   }
 }
 extern "C" void hostsim_es_asss_f32(ARGS(float)) { run_es_asss<float>(PASS); }
