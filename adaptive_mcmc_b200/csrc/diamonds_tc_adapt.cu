@@ -16,7 +16,9 @@
 // so the factor is read once and written once per step.  The helper warps run one step ahead and only
 // produce the draws (z, u).
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <utility>
 #include <vector>
 #include "diamonds_tc.cuh"
@@ -195,7 +197,7 @@ __device__ __forceinline__ float tc_column_pass(float* __restrict__ col, const f
 // proposal -> A' row (split bf16), scalar part of U', shadow position buffer.  Returns via references.
 __device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const float* __restrict__ cref, int64_t C, double rss_ref,
                                                  unsigned char* sA, int g, int row, uint64_t* a_ready_g, double n_rows, double cst,
-                                                 double& Up_part, double& inv2var) {
+                                                 double& Up_part, double& inv2var, double& rss_part) {
   float dq = 0.f;
   uint32_t hi[TC_KC], lo[TC_KC];  // bf16 bit patterns in the low halves
   float qr[TC_KC], g2[TC_KC];
@@ -235,7 +237,8 @@ __device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const 
   const float ti = (xp[0] - 8.f) * 0.1f, ts = __expf(s) * 0.1f;
   inv2var = 0.5 * exp(-2.0 * (double)s);
   Up_part = (double)(0.5f * sb + 2.f * log1pf(ti * ti * (1.f / 3.f)) + 2.f * log1pf(ts * ts * (1.f / 3.f))) +
-            (n_rows - 1.0) * (double)s + cst + inv2var * (rss_ref - (double)dq);
+            (n_rows - 1.0) * (double)s + cst;
+  rss_part = rss_ref - (double)dq;  // + sum m^2 from the GEMM = RSS; assembled and clamped at 0 by the caller
 }
 
 // Warp roles: warps 0-7 = the two sampler warpgroups (TMEM epilogue + per-chain state), warp 8 = TMA producer,
@@ -275,9 +278,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the role branches are warp-uniform
-  const int per = p.n_groups / (int)gridDim.x, rem = p.n_groups % (int)gridDim.x;
-  const int g_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
-  const int g_count = per + ((int)blockIdx.x < rem ? 1 : 0);
+  // Group ownership is interleaved: CTA b owns groups b, b + grid, b + 2 grid, ...  The first two groups of every CTA
+  // are then the first 2 * grid groups of the factor buffer -- the contiguous prefix the host pins in L2 -- and both
+  // streams of a CTA (groups 0, 2 / groups 1, 3) get one pinned and one streaming group each.
+  const int g_count = (int)blockIdx.x < p.n_groups ? (p.n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -308,8 +312,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
 #define TC_ROUND_BEGIN                                   \
   for (int rnd = 0; rnd < n_rounds; ++rnd) {             \
     const int G = min(TC_GR, g_count - rnd * TC_GR);     \
-    const int g0 = g_begin + rnd * TC_GR;                \
-    (void)g0;
+    const int64_t g0 = (int64_t)blockIdx.x + (int64_t)rnd * TC_GR * gridDim.x; \
+    const int64_t gs = gridDim.x;                        \
+    (void)g0; (void)gs;
 #define TC_ROUND_END                                     \
     a_it += (uint32_t)p.n_steps;                         \
   }
@@ -375,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
         for (int g = 0; g < G; ++g) {
           mbar_wait(&v_empty[g], ((a_it + (uint32_t)st) & 1) ^ 1);
           for (int row = ht; row < TC_M; row += 32 * TC_HELP_WARPS) {
-            const int64_t c = (int64_t)(g0 + g) * TC_M + row;
+            const int64_t c = (g0 + g * gs) * TC_M + row;
             const int64_t cc = c < p.C ? c : (p.C - 1);
             float* vrow = sV + (size_t)g * 27 * TC_M + row;
             if (EXTERNAL) {
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
       // The two chains a thread owns (groups 2*half and 2*half+1) are served by ONE copy of the code: the loop
       // over them is rolled and the per-chain scalars are swapped at its end, so they stay in registers.
       float UcurA = 0.f, UcurB = 0.f, maccA = 0.f, maccB = 0.f, lamA = 0.f, lamB = 0.f, uaccA = 2.f, uaccB = 2.f;
-      double UppA = 0.0, UppB = 0.0, i2vA = 0.0, i2vB = 0.0;
+      double UppA = 0.0, UppB = 0.0, i2vA = 0.0, i2vB = 0.0, rssA = 0.0, rssB = 0.0;
       int curA = 0, curB = 0;
       int64_t until_collect = p.collect_start + p.thinning;
       int64_t sidx = 0;
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
       for (int rep = 0; rep < 2; ++rep) {
         const int g = half + 2 * rep;
         if (g < G) {
-          const int64_t c = (int64_t)(g0 + g) * TC_M + row;
+          const int64_t c = (g0 + g * gs) * TC_M + row;
           const int64_t cc = c < p.C ? c : (p.C - 1);
           UcurA = p.pe[cc]; maccA = p.macc[cc]; lamA = ap.lam[cc];
         }
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
         for (int rep = 0; rep < 2; ++rep) {
           const int g = half + 2 * rep;
           if (g < G) {
-            const int64_t c = (int64_t)(g0 + g) * TC_M + row;
+            const int64_t c = (g0 + g * gs) * TC_M + row;
             const bool live = c < p.C;
             const int64_t cc = live ? c : (p.C - 1);
             float w[TC_D], acc[TC_D];
@@ -479,7 +484,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
             if (st >= 0) {
               // ---- accept / reject (arwmh.py:170-178)
               const float mine = rep ? mine1 : mine0;
-              float Up = (float)(UppA + i2vA * (double)mine);
+              // RSS is a sum of squares: assembled first and clamped at 0, so that the cancellation error of a far-away
+              // proposal (the reference's start makes chains jump by hundreds, with e^{-2s} ~ 1e300) cannot turn into a
+              // large NEGATIVE energy, which would be accepted and never left
+              const double rss = rssA + (double)mine;
+              float Up = (float)(UppA + i2vA * (rss > 0.0 ? rss : 0.0));
               if (Up != Up) Up = INFINITY;
               const float e = __expf(UcurA - Up);
               const float alpha = (e > 1.f) ? 1.f : e;
@@ -525,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
               for (int k = 0; k < TC_D; ++k) w[k] = 0.f;
             }
             const float* zn = sV + (size_t)g * 27 * TC_M + row;
-            float* fcol = ap.ldl + (int64_t)(g0 + g) * (TC_NE * TC_M) + row;
+            float* fcol = ap.ldl + (g0 + g * gs) * (TC_NE * TC_M) + row;
             TC_T(3);
             if (last) {
               const float ss = tc_column_pass<true>(fcol, zn, false, upd, w, gamma, el_old, el_new, acc);
@@ -548,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
               }
               uaccA = zn[26 * TC_M];
               mbar_arrive(&v_empty[g]);
-              tc_emit_proposal(xp, ap.cref + cc, p.C, ap.crss[cc], sA, g, row, &a_ready[g], (double)p.n_rows, p.cst, UppA, i2vA);
+              tc_emit_proposal(xp, ap.cref + cc, p.C, ap.crss[cc], sA, g, row, &a_ready[g], (double)p.n_rows, p.cst, UppA, i2vA, rssA);
               TC_T(6);
             }
           }
@@ -560,6 +569,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
             tf = uaccA; uaccA = uaccB; uaccB = tf;
             td = UppA; UppA = UppB; UppB = td;
             td = i2vA; i2vA = i2vB; i2vB = td;
+            td = rssA; rssA = rssB; rssB = td;
             ti = curA; curA = curB; curB = ti;
           }
         }
@@ -570,7 +580,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
       for (int rep = 0; rep < 2; ++rep) {
         const int g = half + 2 * rep;
         if (g < G) {
-          const int64_t c = (int64_t)(g0 + g) * TC_M + row;
+          const int64_t c = (g0 + g * gs) * TC_M + row;
           if (c < p.C) {
             p.pe[c] = UcurA;
             p.macc[c] = maccA;
@@ -650,6 +660,38 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
   // RSS_ref - 2 d.g + sum m^2 grows with |d|^2), so the run is cut into segments of at most kSegment steps and every
   // chain's reference point is moved to its current position before each of them.  Per-chain state stays in the
   // LDL^T blocks across the segments.
+  // L2 residency: at 65,536 chains the 92 MB of factors plus ~35 MB of positions / means / reference points exceed
+  // the 126 MB L2 by a little, and a cyclic sweep through slightly-too-much data gets no hits from an LRU-like policy
+  // (ncu: the whole factor is re-streamed from HBM every step).  The factors of the first two groups of every CTA
+  // (a contiguous prefix of the buffer, see the kernel) are pinned with an access-policy window; the rest streams.
+  size_t pinned = 0;
+  {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    const size_t total = (size_t)ap.p.n_groups * TC_NE * TC_M * sizeof(float);
+    double per_cta = 2.0;  // pinned groups per CTA (tunable for experiments: AMCMC_TC_PIN_GROUPS)
+    if (const char* e = getenv("AMCMC_TC_PIN_GROUPS")) per_cta = atof(e);
+    size_t want = (size_t)(per_cta * grid) * TC_NE * TC_M * sizeof(float);
+    if (getenv("AMCMC_TC_PIN_VERBOSE")) fprintf(stderr, "[amcmc] L2 pin: max_persist %d MB, max_window %d MB, want %zu MB\n", max_persist >> 20, max_window >> 20, want >> 20);
+    if (want > total) want = total;
+    if (want > (size_t)max_persist) want = (size_t)max_persist;
+    if (want > (size_t)max_window) want = (size_t)max_window;
+    if (total > ((size_t)48 << 20) && want > 0 && !getenv("AMCMC_TC_NO_L2_PIN")) {  // small batches fit in L2 anyway
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof(attr));
+      attr.accessPolicyWindow.base_ptr = ap.ldl;
+      attr.accessPolicyWindow.num_bytes = want;
+      attr.accessPolicyWindow.hitRatio = 1.0f;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess &&
+          cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess)
+        pinned = want;
+      else
+        cudaGetLastError();  // pinning is an optimisation: run without it
+    }
+  }
   const TcParams full = ap.p;
   int64_t seg = kSegment;
   if (const char* e = getenv("AMCMC_TC_SEGMENT")) {  // test hook: exercise the segment bookkeeping in short runs
@@ -676,7 +718,14 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     if ((rc = check_cuda(cudaGetLastError(), "diamonds_tc_adapt_kernel launch"))) return rc;
   }
   tc_ldl_to_chol_kernel<<<ap.p.n_groups, TC_M, 0, s>>>(ap.ldl, (float*)st->scale, C);
-  return check_cuda(cudaGetLastError(), "tc_ldl_to_chol_kernel launch");
+  rc = check_cuda(cudaGetLastError(), "tc_ldl_to_chol_kernel launch");
+  if (pinned) {  // drop the window for whatever runs next on this stream
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+  }
+  return rc;
 }
 
 }  // namespace amcmc

@@ -3,7 +3,7 @@ import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os
 import adaptive_mcmc_b200 as am
 from adaptive_mcmc_b200 import models, _lib
 data=models.synthetic_diamonds()
-for C in (4096, 16384, 65536):
+for C in (65536, 131072):
     for impl,name,T in ((_lib.IMPL_TENSOR,'tc-adapt',400),(_lib.IMPL_BLOCK,'block',20)):
         s=am.ARWMH(models.diamonds,num_chains=C); s.impl=impl
         st=s.init(0,num_warmup=0,init_params=None,model_kwargs=data)

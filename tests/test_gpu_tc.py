@@ -407,3 +407,26 @@ def test_diamonds_tc_adaptive_rejects_blown_up_proposals(diamonds_data):
     assert same.mean() > 0.95
     sel = torch.from_numpy(same).to(res[_lib.IMPL_TENSOR][1].device)
     assert (res[_lib.IMPL_TENSOR][1][:, sel] - res[_lib.IMPL_BLOCK][1][:, sel]).abs().max() < 1e-4
+
+
+def test_diamonds_tc_adaptive_survives_runaway_proposals(diamonds_data):
+    """Regression: from the reference's start a chain can jump by hundreds within ten steps (chain 83339 of seed 0:
+    log sigma -1.7 -> 0.7 -> 17.7, in the exact block kernel too) and then propose log sigma = -349, where
+    e^{-2s} ~ 1e303.  RSS_ref - 2 D.g + sum m^2 cancels catastrophically there; assembled naively its negative value
+    times e^{-2s} became U' = -inf, which was accepted and never left.  RSS is now clamped at 0 before the scaling."""
+    off, j = 83328, 11
+    res = {}
+    for impl in (_lib.IMPL_TENSOR, _lib.IMPL_BLOCK):
+        s = am.ARWMH(models.diamonds, num_chains=128, chain_offset=off)
+        s.impl = impl
+        st = s.init(0, num_warmup=0, init_params=None, model_kwargs=diamonds_data)
+        b = am.ChainBatch.from_state(s.potential, st, copy=False)
+        b.set_dense_scale(torch.eye(26) * 0.002)
+        raw = s.run_batch(b, 60, collect=("z", "potential_energy"), record_accept=True)
+        res[impl] = (raw["accept"].cpu().numpy().astype(bool), raw["potential_energy"].cpu().numpy(), b)
+    acc_t, pe_t, b_t = res[_lib.IMPL_TENSOR]
+    acc_b, pe_b, _ = res[_lib.IMPL_BLOCK]
+    assert np.isfinite(pe_t).all() and torch.isfinite(b_t.z).all() and torch.isfinite(b_t.scale).all()
+    assert np.abs(pe_b[:, j]).max() > 1e5                                                             # this chain does jump
+    np.testing.assert_array_equal(acc_t[:12, j], acc_b[:12, j])                                       # incl. the rejection at step 10
+    assert (acc_t[:10] == acc_b[:10]).all(axis=0).mean() > 0.9
