@@ -35,6 +35,7 @@ struct TcAdaptParams {
   float* asc;        // [C]
   int64_t num_warmup;
   float lr_decay, target, eps;
+  int rnd_begin, rnd_end;  // rounds (sets of TC_GR groups per CTA) served by this launch
 };
 
 __device__ __forceinline__ int tri_f(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -305,12 +306,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_rounds = (g_count + TC_GR - 1) / TC_GR;
+  const int n_rounds_all = (g_count + TC_GR - 1) / TC_GR;
+  const int n_rounds = n_rounds_all < ap.rnd_end ? n_rounds_all : ap.rnd_end;
   uint32_t x_it = 0, acc_it = 0, a_it = 0;
   uint32_t ks0 = 0, ks1 = 0;  // MMA warp: accumulators issued so far per stream
 
 #define TC_ROUND_BEGIN                                   \
-  for (int rnd = 0; rnd < n_rounds; ++rnd) {             \
+  for (int rnd = ap.rnd_begin; rnd < n_rounds; ++rnd) {  \
     const int G = min(TC_GR, g_count - rnd * TC_GR);     \
     const int64_t g0 = (int64_t)blockIdx.x + (int64_t)rnd * TC_GR * gridDim.x; \
     const int64_t gs = gridDim.x;                        \
@@ -664,34 +666,40 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
   // the 126 MB L2 by a little, and a cyclic sweep through slightly-too-much data gets no hits from an LRU-like policy
   // (ncu: the whole factor is re-streamed from HBM every step).  The factors of the first two groups of every CTA
   // (a contiguous prefix of the buffer, see the kernel) are pinned with an access-policy window; the rest streams.
-  size_t pinned = 0;
-  {
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-    const size_t total = (size_t)ap.p.n_groups * TC_NE * TC_M * sizeof(float);
-    double per_cta = 2.0;  // pinned groups per CTA (tunable for experiments: AMCMC_TC_PIN_GROUPS)
-    if (const char* e = getenv("AMCMC_TC_PIN_GROUPS")) per_cta = atof(e);
-    size_t want = (size_t)(per_cta * grid) * TC_NE * TC_M * sizeof(float);
-    if (getenv("AMCMC_TC_PIN_VERBOSE")) fprintf(stderr, "[amcmc] L2 pin: max_persist %d MB, max_window %d MB, want %zu MB\n", max_persist >> 20, max_window >> 20, want >> 20);
-    if (want > total) want = total;
+  // (when a CTA serves more than TC_GR groups it does so in rounds; every round is its own launch, with the window
+  // moved to the first two groups of that round -- group ids of local index l are the contiguous range [l grid, (l+1) grid))
+  int max_persist = 0, max_window = 0;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  const size_t group_bytes = (size_t)TC_NE * TC_M * sizeof(float);
+  const size_t total_bytes = (size_t)ap.p.n_groups * group_bytes;
+  double per_cta = 2.0;  // pinned groups per CTA (tunable for experiments: AMCMC_TC_PIN_GROUPS)
+  if (const char* e = getenv("AMCMC_TC_PIN_GROUPS")) per_cta = atof(e);
+  const bool want_pin = total_bytes > ((size_t)48 << 20) && !getenv("AMCMC_TC_NO_L2_PIN");  // small batches fit in L2 anyway
+  bool pinned = false;
+  int pinned_round = -1;
+  auto pin_round = [&](int rnd) {
+    if (!want_pin || rnd == pinned_round) return;  // (a single-round run sets the window once for all its segments)
+    pinned_round = rnd;
+    const size_t first = (size_t)rnd * TC_GR * grid;                 // first group of the round
+    if (first >= (size_t)ap.p.n_groups) return;
+    size_t want = (size_t)(per_cta * grid) * group_bytes;
+    if (first * group_bytes + want > total_bytes) want = total_bytes - first * group_bytes;
     if (want > (size_t)max_persist) want = (size_t)max_persist;
     if (want > (size_t)max_window) want = (size_t)max_window;
-    if (total > ((size_t)48 << 20) && want > 0 && !getenv("AMCMC_TC_NO_L2_PIN")) {  // small batches fit in L2 anyway
-      cudaStreamAttrValue attr;
-      memset(&attr, 0, sizeof(attr));
-      attr.accessPolicyWindow.base_ptr = ap.ldl;
-      attr.accessPolicyWindow.num_bytes = want;
-      attr.accessPolicyWindow.hitRatio = 1.0f;
-      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess &&
-          cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess)
-        pinned = want;
-      else
-        cudaGetLastError();  // pinning is an optimisation: run without it
-    }
-  }
+    if (want == 0) return;
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = (char*)ap.ldl + first * group_bytes;
+    attr.accessPolicyWindow.num_bytes = want;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (!pinned && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) pinned = true;
+    else cudaGetLastError();  // pinning is an optimisation: run without it
+  };
+  const int rounds_max = ((ap.p.n_groups + grid - 1) / grid + TC_GR - 1) / TC_GR;
   const TcParams full = ap.p;
   int64_t seg = kSegment;
   if (const char* e = getenv("AMCMC_TC_SEGMENT")) {  // test hook: exercise the segment bookkeeping in short runs
@@ -713,9 +721,14 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     if (full.normals) p.normals = full.normals + s0 * TC_D * C;
     if (full.uniforms) p.uniforms = full.uniforms + s0 * C;
     tc_chain_ref_kernel<<<(unsigned)((C + 127) / 128), 128, 0, s>>>(ex->gram, (const float*)st->z, C, ex->cref, ex->crss);
-    if (a->rng_mode == AMCMC_RNG_EXTERNAL) diamonds_tc_adapt_kernel<true><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
-    else diamonds_tc_adapt_kernel<false><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
-    if ((rc = check_cuda(cudaGetLastError(), "diamonds_tc_adapt_kernel launch"))) return rc;
+    for (int rnd = 0; rnd < rounds_max; ++rnd) {
+      pin_round(rnd);
+      ap.rnd_begin = rnd;
+      ap.rnd_end = rnd + 1;
+      if (a->rng_mode == AMCMC_RNG_EXTERNAL) diamonds_tc_adapt_kernel<true><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
+      else diamonds_tc_adapt_kernel<false><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
+      if ((rc = check_cuda(cudaGetLastError(), "diamonds_tc_adapt_kernel launch"))) return rc;
+    }
   }
   tc_ldl_to_chol_kernel<<<ap.p.n_groups, TC_M, 0, s>>>(ap.ldl, (float*)st->scale, C);
   rc = check_cuda(cudaGetLastError(), "tc_ldl_to_chol_kernel launch");
