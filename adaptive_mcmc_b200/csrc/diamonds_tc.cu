@@ -404,6 +404,7 @@ int create_diamonds_tc(amcmc_model* m, const double* X, int64_t n, int K, const 
   }
   const int n_tiles = (int)((n + TC_TILE_N - 1) / TC_TILE_N);
   std::vector<uint16_t> canon((size_t)n_tiles * (TC_TILE_BYTES / 2), 0);
+  std::vector<uint16_t> canon64((size_t)n_tiles * (TC_TILE_N * 64), 0);
   std::vector<double> gram(TC_KC * TC_KC + TC_KC + 1, 0.0);
   std::vector<double> x1(TC_KC);
   for (int64_t r = 0; r < n; ++r) {
@@ -416,6 +417,7 @@ int create_diamonds_tc(amcmc_model* m, const double* X, int64_t n, int K, const 
     gram[TC_KC * TC_KC + TC_KC] += Y[r] * Y[r];
     const int tile = (int)(r / TC_TILE_N), rr = (int)(r % TC_TILE_N);
     uint16_t* t = canon.data() + (size_t)tile * (TC_TILE_BYTES / 2);
+    uint16_t* t64 = canon64.data() + (size_t)tile * (TC_TILE_N * 64);
     for (int k = 0; k < TC_KC; ++k) {
       const float xf = (float)x1[k];
       const uint16_t hi = host_f2bf(xf);
@@ -423,6 +425,8 @@ int create_diamonds_tc(amcmc_model* m, const double* X, int64_t n, int K, const 
       t[canon_off(rr, k, TC_TILE_N) / 2] = hi;               // pairs with D_hi
       t[canon_off(rr, TC_KC + k, TC_TILE_N) / 2] = hi;       // pairs with D_lo
       t[canon_off(rr, 2 * TC_KC + k, TC_TILE_N) / 2] = lo;   // pairs with D_hi
+      t64[canon_off(rr, k, TC_TILE_N) / 2] = hi;
+      t64[canon_off(rr, 32 + k, TC_TILE_N) / 2] = lo;
     }
   }
   DiamondsTcExtra* ex = (DiamondsTcExtra*)calloc(1, sizeof(DiamondsTcExtra));
@@ -436,6 +440,8 @@ int create_diamonds_tc(amcmc_model* m, const double* X, int64_t n, int K, const 
   if ((rc = check_cuda(cudaMalloc(&ex->ident, 352 * 4), "cudaMalloc(ident)"))) return rc;
   if ((rc = check_cuda(cudaMalloc(&ex->zero, 4), "cudaMalloc(zero)"))) return rc;
   if ((rc = check_cuda(cudaMemcpy(ex->Xcanon, canon.data(), canon.size() * 2, cudaMemcpyHostToDevice), "cudaMemcpy"))) return rc;
+  if ((rc = check_cuda(cudaMalloc(&ex->Xcanon64, canon64.size() * 2), "cudaMalloc(Xcanon64)"))) return rc;
+  if ((rc = check_cuda(cudaMemcpy(ex->Xcanon64, canon64.data(), canon64.size() * 2, cudaMemcpyHostToDevice), "cudaMemcpy"))) return rc;
   if ((rc = check_cuda(cudaMemcpy(ex->gram, gram.data(), gram.size() * 8, cudaMemcpyHostToDevice), "cudaMemcpy"))) return rc;
   m->extra = ex;
   return AMCMC_OK;
@@ -445,6 +451,7 @@ void destroy_diamonds_tc(amcmc_model* m) {
   DiamondsTcExtra* ex = (DiamondsTcExtra*)m->extra;
   if (!ex) return;
   if (ex->Xcanon) cudaFree(ex->Xcanon);
+  if (ex->Xcanon64) cudaFree(ex->Xcanon64);
   if (ex->gram) cudaFree(ex->gram);
   if (ex->ref) cudaFree(ex->ref);
   if (ex->xprop) cudaFree(ex->xprop);

@@ -34,6 +34,7 @@ constexpr int REF_FLOATS = 64 + TC_D * REF_SLD;
 
 struct DiamondsTcExtra {
   uint16_t* Xcanon;  // [n_tiles][TC_TILE_BYTES/2] bf16, canonical UMMA tile order
+  uint16_t* Xcanon64;  // [n_tiles][256 x 64] bf16: [X_hi (25 + 7 zeros) | X_lo (25 + 7 zeros)], for the per-chain-adaptive kernel
   int n_tiles;
   double* gram;      // G[25*25] = X1^T X1, h[25] = X1^T Y, yy   (fp64, device)
   float* ref;        // [REF_FLOATS] device

@@ -31,6 +31,7 @@ struct TcAdaptParams {
   float* ldl;        // [n_groups][351][128]  LDL^T blocks
   const float* cref; // [50][C] per-chain reference point of the centred GEMM: q_ref (25), 2 g (25)
   const double* crss;  // [C] RSS at the reference point
+  const uint16_t* Xcanon64;  // design-matrix tiles in this kernel's K = 64 layout
   float* lam;        // [C]
   float* asc;        // [C]
   int64_t num_warmup;
@@ -195,6 +196,26 @@ __device__ __forceinline__ float tc_column_pass(float* __restrict__ col, const f
   return x.ss;
 }
 
+// Operand layout of THIS kernel: K = 64 for both operands, A' = [D_hi (25 + 7 zeros) | D_lo (25 + 7 zeros)],
+// B' = [X_hi | X_lo] likewise, and the three significant cross terms come from six K = 16 MMAs whose descriptors pick
+// the 16-column chunks (A, B) = (0,0) (1,1) | (2,0) (3,1) | (0,2) (1,3)  =  D_hi X_hi + D_lo X_hi + D_hi X_lo.
+// Compared with the K = 80 concatenation of diamonds_tc.cu this is one more MMA per accumulator (768 instead of 640
+// tensor cycles) but 20 % fewer bytes per design-matrix tile -- and this kernel is bound by SM <-> L2 traffic
+// (each stream re-reads every tile for only two groups), not by the tensor pipe.
+constexpr int TCA_K = 64;
+constexpr int TCA_TILE_BYTES = TC_TILE_N * TCA_K * 2;  // 32768
+constexpr int TCA_A_BYTES = TC_M * TCA_K * 2;          // 16384
+constexpr int TCA_STAGES = 2;                          // design-matrix tiles in flight (a third stage was measured: no gain)
+struct TcaSmem {
+  static constexpr int OFF_X = 0;                                // TCA_STAGES stages
+  static constexpr int OFF_A = TCA_STAGES * TCA_TILE_BYTES;      // TC_GR groups
+  static constexpr int OFF_BAR = OFF_A + TC_GR * TCA_A_BYTES;    // x_full[2], x_empty[2], (4 unused), a_ready, v_full, v_empty
+  static constexpr int OFF_TMEM = OFF_BAR + TcSmem::N_BAR * 8;
+  static constexpr int OFF_ACCBAR = OFF_TMEM + 16;               // acc_full[4], acc_empty[4]
+  static constexpr int OFF_V = OFF_ACCBAR + 64;                  // float [TC_GR][27][TC_M]
+  static constexpr int BYTES = OFF_V + TC_GR * 27 * TC_M * 4;
+};
+
 // proposal -> A' row (split bf16), scalar part of U', shadow position buffer.  Returns via references.
 __device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const float* __restrict__ cref, int64_t C, double rss_ref,
                                                  unsigned char* sA, int g, int row, uint64_t* a_ready_g, double n_rows, double cst,
@@ -215,13 +236,11 @@ __device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const 
     hi[k] = h;
     lo[k] = f2bf(dlt - bf2f(h));
   }
-  // K' layout: [hi(25) | lo(25) | hi(25) | 0(5)]
-  auto elem = [&](int k) -> uint32_t {
-    return k < TC_KC ? hi[k] : (k < 2 * TC_KC ? lo[k - TC_KC] : (k < 3 * TC_KC ? hi[k - 2 * TC_KC] : 0u));
-  };
-  unsigned char* arow = sA + g * TC_A_BYTES + (row >> 3) * 128 + (row & 7) * 16;
+  // K layout: [hi(25) | 0(7) | lo(25) | 0(7)]
+  auto elem = [&](int k) -> uint32_t { return k < TC_KC ? hi[k] : (k < 32 ? 0u : (k < 32 + TC_KC ? lo[k - 32] : 0u)); };
+  unsigned char* arow = sA + g * TCA_A_BYTES + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
-  for (int kc = 0; kc < TC_KP / 8; ++kc) {
+  for (int kc = 0; kc < TCA_K / 8; ++kc) {
     uint4 v;
     v.x = elem(8 * kc) | (elem(8 * kc + 1) << 16);
     v.y = elem(8 * kc + 2) | (elem(8 * kc + 3) << 16);
@@ -262,20 +281,20 @@ template <bool EXTERNAL>
 __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const TcAdaptParams ap) {
   const TcParams& p = ap.p;
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* sX = smem + TcSmem::OFF_X;
-  unsigned char* sA = smem + TcSmem::OFF_A;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcSmem::OFF_BAR);
-  uint64_t* x_full = bars;
-  uint64_t* x_empty = bars + 2;
+  unsigned char* sX = smem + TcaSmem::OFF_X;
+  unsigned char* sA = smem + TcaSmem::OFF_A;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcaSmem::OFF_BAR);
+  uint64_t* x_full = bars;          // [TCA_STAGES] (the slots of the unused acc barriers of the shared layout follow)
+  uint64_t* x_empty = bars + 4;     // [TCA_STAGES]
   // accumulator hand-off, per stream and TMEM buffer: [stream * 2 + buffer].  Both streams use both buffers; a
   // waiter on an mbarrier parity may lag at most one phase, so the streams cannot share one barrier ring.
-  uint64_t* acc_full = reinterpret_cast<uint64_t*>(smem + TcSmem::OFF_EXCH);
+  uint64_t* acc_full = reinterpret_cast<uint64_t*>(smem + TcaSmem::OFF_ACCBAR);
   uint64_t* acc_empty = acc_full + 4;
   uint64_t* a_ready = bars + 8;
   uint64_t* v_full = bars + 8 + TC_GR;
   uint64_t* v_empty = bars + 8 + 2 * TC_GR;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcSmem::OFF_TMEM);
-  float* sV = reinterpret_cast<float*>(smem + TcSmem::OFF_V);  // [TC_GR][27][TC_M]: next draws z[26], u
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TcaSmem::OFF_TMEM);
+  float* sV = reinterpret_cast<float*>(smem + TcaSmem::OFF_V);  // [TC_GR][27][TC_M]: next draws z[26], u
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the role branches are warp-uniform
@@ -285,7 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
   const int g_count = (int)blockIdx.x < p.n_groups ? (p.n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < TCA_STAGES; ++s) {
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
     }
@@ -330,10 +349,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
         const int n_streams = G > 1 ? 2 : 1;  // one sweep over the design matrix per stream and step
         for (int64_t sweep = 0; sweep < p.n_steps * n_streams; ++sweep)
           for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
-            const int s = x_it & 1;
-            mbar_wait(&x_empty[s], ((x_it >> 1) & 1) ^ 1);
-            mbar_arrive_expect_tx(&x_full[s], TC_TILE_BYTES);
-            tma_load_1d(sX + s * TC_TILE_BYTES, p.Xcanon + (size_t)tile * (TC_TILE_BYTES / 2), TC_TILE_BYTES, &x_full[s]);
+            const int s = x_it % TCA_STAGES;
+            mbar_wait(&x_empty[s], ((x_it / TCA_STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(&x_full[s], TCA_TILE_BYTES);
+            tma_load_1d(sX + s * TCA_TILE_BYTES, ap.Xcanon64 + (size_t)tile * (TCA_TILE_BYTES / 2), TCA_TILE_BYTES, &x_full[s]);
           }
       }
       TC_ROUND_END
@@ -346,8 +365,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
         for (int strm = 0; strm < 2; ++strm) {  // stream = groups strm, strm + 2 (see the sampler warps)
           if (strm >= G) break;
           for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
-            const int s = x_it & 1;
-            mbar_wait(&x_full[s], (x_it >> 1) & 1);
+            const int s = x_it % TCA_STAGES;
+            mbar_wait(&x_full[s], (x_it / TCA_STAGES) & 1);
             for (int g = strm; g < G; g += 2) {
               if (tile == 0) mbar_wait(&a_ready[g], (a_it + (uint32_t)st) & 1);
               uint32_t& k = strm ? ks1 : ks0;
@@ -358,11 +377,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
               if (u_own) mbar_wait(&acc_empty[strm * 2 + b], (u_own - 1) & 1);
               if (u_oth) mbar_wait(&acc_empty[(strm ^ 1) * 2 + b], (u_oth - 1) & 1);
               tc_fence_after();
-              const uint32_t a_base = smem_u32(sA + g * TC_A_BYTES), b_base = smem_u32(sX + s * TC_TILE_BYTES);
+              const uint32_t a_base = smem_u32(sA + g * TCA_A_BYTES), b_base = smem_u32(sX + s * TCA_TILE_BYTES);
 #pragma unroll
-              for (int ks = 0; ks < TC_KP / 16; ++ks) {
-                const uint64_t da = make_smem_desc(a_base + 2 * ks * a_kstride, a_kstride, 128);
-                const uint64_t db = make_smem_desc(b_base + 2 * ks * b_kstride, b_kstride, 128);
+              for (int ks = 0; ks < 6; ++ks) {
+                const int ia = ks < 4 ? ks : ks - 4;              // A chunks 0 1 | 2 3 | 0 1   (D_hi | D_lo | D_hi)
+                const int ib = ks < 2 ? ks : ks - 2;              // B chunks 0 1 | 0 1 | 2 3   (X_hi | X_hi | X_lo)
+                const uint64_t da = make_smem_desc(a_base + 2 * ia * a_kstride, a_kstride, 128);
+                const uint64_t db = make_smem_desc(b_base + 2 * ib * b_kstride, b_kstride, 128);
                 umma_bf16(tmem_base + (uint32_t)(b * TC_TILE_N), da, db, idesc, ks > 0);
               }
               umma_commit(&acc_full[strm * 2 + b]);
@@ -646,6 +667,7 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     ex->cref_cap = C;
   }
   ap.cref = ex->cref;
+  ap.Xcanon64 = ex->Xcanon64;
   ap.crss = ex->crss;
   tc_chol_to_ldl_kernel<<<ap.p.n_groups, TC_M, 0, s>>>((const float*)st->scale, ap.ldl, C);
   int dev = 0, sms = 148;
@@ -656,8 +678,8 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     if (v > 0 && v < sms) sms = v;
   }
   const int grid = ap.p.n_groups < sms ? ap.p.n_groups : sms;
-  if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_adapt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
-  if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_adapt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
+  if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_adapt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcaSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
+  if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_adapt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcaSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
   // The centred GEMM is accurate while a chain is close to its reference point (the cancellation in
   // RSS_ref - 2 d.g + sum m^2 grows with |d|^2), so the run is cut into segments of at most kSegment steps and every
   // chain's reference point is moved to its current position before each of them.  Per-chain state stays in the
@@ -725,8 +747,8 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
       pin_round(rnd);
       ap.rnd_begin = rnd;
       ap.rnd_end = rnd + 1;
-      if (a->rng_mode == AMCMC_RNG_EXTERNAL) diamonds_tc_adapt_kernel<true><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
-      else diamonds_tc_adapt_kernel<false><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(ap);
+      if (a->rng_mode == AMCMC_RNG_EXTERNAL) diamonds_tc_adapt_kernel<true><<<grid, TC_THREADS, TcaSmem::BYTES, s>>>(ap);
+      else diamonds_tc_adapt_kernel<false><<<grid, TC_THREADS, TcaSmem::BYTES, s>>>(ap);
       if ((rc = check_cuda(cudaGetLastError(), "diamonds_tc_adapt_kernel launch"))) return rc;
     }
   }
