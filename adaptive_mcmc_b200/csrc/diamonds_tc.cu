@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
       for (int64_t st = 0; st < p.n_steps; ++st) {
         // The handful of scalar terms of U' is assembled in float64: N*s and the normalisation constant are
         // O(1e4) and would cost ~1e-3 absolute in fp32 (40 DFMA-class ops per chain-step: negligible).
-        double Up_part[2], inv2var[2], rss_part[2];  // U' = Up_part + inv2var * max(rss_part + sum m^2, 0)
+        double Up_part[2], inv2var[2];  // U' = Up_part + inv2var * max(RSS_ref - dq + sum m^2, 0)
+        float dqv[2];
         float uacc[2], rss[TC_GR];
 #pragma unroll
         for (int g = 0; g < TC_GR; ++g) rss[g] = 0.f;
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
 #pragma unroll
         for (int o = 0; o < 2; ++o) {
           const int g = 2 * half + o;
-          Up_part[o] = 0.0; inv2var[o] = 0.0; rss_part[o] = 0.0; uacc[o] = 2.f;
+          Up_part[o] = 0.0; inv2var[o] = 0.0; dqv[o] = 0.f; uacc[o] = 2.f;
           if (g < G) {
             const int64_t c = (int64_t)(g0 + g) * TC_M + row;
             const bool live = c < p.C;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
             // U' = 1/2 sum b^2 + 2 log1p(ti^2/3) + 2 log1p(ts^2/3) + (N-1) s + cst + e^{-2s}/2 (RSS_ref - 2 D.g + sum m^2)
             Up_part[o] = (double)(0.5f * sb + 2.f * log1pf(ti * ti * (1.f / 3.f)) + 2.f * log1pf(ts * ts * (1.f / 3.f))) +
                          ((double)p.n_rows - 1.0) * (double)s + p.cst;
-            rss_part[o] = *reinterpret_cast<const double*>(sRef + REF_RSS) - (double)dq;
+            dqv[o] = dq;
           }
         }
         // ---- likelihood: sum_n m_n^2 from the TMEM accumulators (this thread's 128 columns of every tile)
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
             if (c < p.C) {
               // RSS is a sum of squares: assembled first and clamped at 0, so that the cancellation error of a
               // far-away proposal (|D| in the hundreds, e^{-2s} ~ 1e300) cannot turn into a large NEGATIVE energy
-              const double rss = rss_part[o] + (double)mine[o];
+              const double rss = (*reinterpret_cast<const double*>(sRef + REF_RSS) - (double)dqv[o]) + (double)mine[o];
               float Up = (float)(Up_part[o] + inv2var[o] * (rss > 0.0 ? rss : 0.0));
               if (Up != Up) Up = INFINITY;
               const float e = __expf(Ucur[o] - Up);
