@@ -47,7 +47,7 @@ def _logistic_potential(x, y):
     return pot
 
 
-def test_plugin_builds_without_a_gpu_and_rejects_bad_source():
+def test_plugin_builds_without_a_gpu_and_rejects_bad_source(built):
     so = custom.build_plugin("t_quadratic", 2, "    return (R)0.5 * (q[0] * q[0] + q[1] * q[1]);")
     import ctypes
     L = ctypes.CDLL(so)
