@@ -231,3 +231,19 @@ def test_asss_sample_Pnx_frozen_kernel():
         ost = ost._replace(adapt_state=oa.ASSSAdaptState(z0.copy(), np.broadcast_to(scale0.numpy(), (C, d, d)).copy()))
         olast, _ = oa.asss_run(ost, potf, T, draws=(nrm, uni), adapt=False)
         np.testing.assert_allclose(b.z.t().cpu().numpy(), olast.z, rtol=1e-6, atol=1e-8)
+
+
+def test_asss_diamonds_through_the_mcmc_driver():
+    """run_diamonds_wasserstein.py 'sss' in miniature: MCMC(ASSS(model)).run(key, **data) with the diamonds model."""
+    data = models.synthetic_diamonds(n=5000, k=25, seed=0)
+    rng = np.random.default_rng(0)
+    q0 = _diamonds_start(data, 32, rng)
+    mcmc = am.MCMC(am.ASSS(models.diamonds, init_strategy=am.init_to_value(torch.from_numpy(q0))), num_warmup=1500, num_samples=1500,
+                   thinning=15, num_chains=32)
+    mcmc.run(1, **data, extra_fields=("potential_energy",))
+    smp = mcmc.get_samples(group_by_chain=True)
+    assert smp["b"].shape == (32, 100, 24) and smp["sigma"].shape == (32, 100)
+    sig = float(smp["sigma"][:, 50:].mean())
+    assert abs(sig - 0.123) < 0.01, sig                      # the data were generated with sigma = 0.123
+    pe = mcmc.get_extra_fields(group_by_chain=True)["potential_energy"]
+    assert torch.isfinite(pe).all() and float(pe[:, -1].median()) < -3.2e3    # at the mode U ~ -3.28e3
