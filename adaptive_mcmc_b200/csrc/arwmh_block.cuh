@@ -15,7 +15,9 @@
 
 namespace amcmc {
 
-constexpr int kBlockThreads = 256;
+constexpr int kBlockThreads = 256;       // many chains: several CTAs per SM
+constexpr int kBlockThreadsWide = 1024;  // few chains (at most one per SM): a wide CTA has 4x the loads in flight
+constexpr int kWideMaxChainsPerSm = 1;
 
 AMCMC_HD int colbase(int j, int d) { return j * (d - 1) - (j * (j - 1)) / 2; }
 // strictly-lower element (i > j) of the column-major packed unit factor
@@ -195,10 +197,9 @@ template <typename R> __device__ __forceinline__ R frob2_warp(const BlockSmem<R>
   return warp_sum(col);
 }
 
-template <class BM, typename R, bool ADAPT, bool EXTERNAL>
-__global__ void __launch_bounds__(kBlockThreads)
+template <class BM, typename R, bool ADAPT, bool EXTERNAL, int NT>
+__global__ void __launch_bounds__(NT)
 arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const int d) {
-  constexpr int NT = kBlockThreads;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BlockSmem<R> sm(smem_raw, d);
   const int tid = threadIdx.x;

@@ -15,10 +15,9 @@ namespace amcmc {
 
 #ifdef __CUDACC__
 
-template <class BM, typename R, bool EXTERNAL, bool ADAPT>
-__global__ void __launch_bounds__(kBlockThreads)
+template <class BM, typename R, bool EXTERNAL, bool ADAPT, int NT>
+__global__ void __launch_bounds__(NT)
 asss_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const int d) {
-  constexpr int NT = kBlockThreads;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BlockSmem<R> sm(smem_raw, d);
   R* zc = sm.z;      // point on the sphere, first d coordinates

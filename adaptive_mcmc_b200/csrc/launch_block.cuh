@@ -1,5 +1,6 @@
 // launch_block.cuh -- host-side launch helpers for the block-per-chain kernels.
 #pragma once
+#include <cstdlib>
 #include "arwmh_block.cuh"
 #include "asss_block.cuh"
 #include "launch_small.cuh"
@@ -24,12 +25,26 @@ int launch_block_run(const BM& m, int d, const amcmc_state* st, const amcmc_run_
   const unsigned grid = (unsigned)st->n_chains;
   const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
   int rc = AMCMC_OK;
+  // Few chains (at most one per SM): one 1024-thread CTA per chain.  The likelihood phase is bound by the loads a CTA
+  // keeps in flight (diamonds: 21 k -> 12 k cycles per step, 14.9 -> 12.5 us per step at 64 chains); with two or more
+  // chains per SM the 256-thread CTAs win (296 chains: 16 us vs 25 us).  Staging half of the design matrix in the
+  // shared memory a wide CTA leaves unused was measured as well and changed nothing.
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool wide = st->n_chains <= (int64_t)kWideMaxChainsPerSm * sms && !getenv("AMCMC_BLOCK_NARROW");
   if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
 #define AMCMC_LA(EX, AD)                                                              \
   do {                                                                                \
-    auto k = asss_block_kernel<BM, R, EX, AD>;                                        \
-    if ((rc = ensure_smem(k, smem))) return rc;                                       \
-    k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);                                \
+    if (wide) {                                                                       \
+      auto k = asss_block_kernel<BM, R, EX, AD, kBlockThreadsWide>;                   \
+      if ((rc = ensure_smem(k, smem))) return rc;                                     \
+      k<<<grid, kBlockThreadsWide, smem, s>>>(m, sv, rv, d);                          \
+    } else {                                                                          \
+      auto k = asss_block_kernel<BM, R, EX, AD, kBlockThreads>;                       \
+      if ((rc = ensure_smem(k, smem))) return rc;                                     \
+      k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);                              \
+    }                                                                                 \
   } while (0)
     if (a->adapt) { if (ext) AMCMC_LA(true, true); else AMCMC_LA(false, true); }
     else          { if (ext) AMCMC_LA(true, false); else AMCMC_LA(false, false); }  // frozen: ASSS.sample_Pnx
@@ -38,9 +53,15 @@ int launch_block_run(const BM& m, int d, const amcmc_state* st, const amcmc_run_
   }
 #define AMCMC_LB(AD, EX)                                                              \
   do {                                                                                \
-    auto k = arwmh_block_kernel<BM, R, AD, EX>;                                       \
-    if ((rc = ensure_smem(k, smem))) return rc;                                       \
-    k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);                                \
+    if (wide) {                                                                       \
+      auto k = arwmh_block_kernel<BM, R, AD, EX, kBlockThreadsWide>;                  \
+      if ((rc = ensure_smem(k, smem))) return rc;                                     \
+      k<<<grid, kBlockThreadsWide, smem, s>>>(m, sv, rv, d);                          \
+    } else {                                                                          \
+      auto k = arwmh_block_kernel<BM, R, AD, EX, kBlockThreads>;                      \
+      if ((rc = ensure_smem(k, smem))) return rc;                                     \
+      k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);                              \
+    }                                                                                 \
   } while (0)
   if (a->adapt) { if (ext) AMCMC_LB(true, true); else AMCMC_LB(true, false); }
   else          { if (ext) AMCMC_LB(false, true); else AMCMC_LB(false, false); }

@@ -62,7 +62,9 @@ def test_diamonds_shared_draws(prec, T, diamonds_data):
     uni = rng.random(size=(T, C)).astype(ndt)
     coll, last = sampler.run(state, T, draws=(torch.from_numpy(nrm), torch.from_numpy(uni)), record_accept=True)
     olast, ocoll = co.arwmh_run(ost, "diamonds", T, draws=(nrm, uni), record_accept=True, num_warmup=20, **diamonds_data)
-    _compare(coll, last, ocoll, olast, tol, 1.0 if prec == "f64" else 0.75)
+    # fp32: both sides sum 5000 residuals in float32, in different orders (the oracle sequentially, the kernel 5 rows per
+    # thread of a 1024-thread CTA + a tree); the fp32 oracle itself is 1.4e-3 away from the fp64 one over these 60 steps
+    _compare(coll, last, ocoll, olast, tol if prec == "f64" else 1.5 * tol, 1.0 if prec == "f64" else 0.75)
 
 
 def test_diamonds_philox_segmentation(diamonds_data):
