@@ -59,7 +59,9 @@ enum amcmc_rng_mode {
 /* Sampler variants: AMCMC_KERNEL_ARWMH = python/kernels/arwmh.py; AMCMC_KERNEL_RAM = BASELINE.json configs[4]
  * (not in the reference); AMCMC_KERNEL_ASSS = python/kernels/asss.py:192-269, the adaptive stereographic slice
  * sampler (state: log_step_size unused, mean_accept_prob carries the mean number of shrinkage iterations;
- * external draws: normals[T][d+1][C], uniforms[T][52][C] = u_t, theta_0/2pi, 50 shrinkage draws). */
+ * external draws: normals[T][d+1][C], uniforms[T][52][C] = u_t, theta_0/2pi, 50 shrinkage draws).  ASSS runs on the
+ * thread-per-chain kernels (STD_NORMAL, EIGHT_SCHOOLS, KIDIQ, CUSTOM) and on the CTA-per-chain kernels (DIAMONDS,
+ * GAUSSIAN with dim <= 32, CUSTOM row models); adapt = 0 is ASSS.sample_Pnx (asss.py:279-315). */
 enum amcmc_kernel_kind { AMCMC_KERNEL_ARWMH = 0, AMCMC_KERNEL_RAM = 1, AMCMC_KERNEL_ASSS = 2 };
 
 typedef struct amcmc_model amcmc_model; /* opaque: device copies of the model data */
@@ -123,7 +125,8 @@ typedef struct amcmc_run_args {
   void* out_potential_energy; /* [S][C] or NULL */
   uint8_t* out_accept;     /* [n_steps][C] accept decisions, or NULL (parity tests) */
   int32_t kernel_kind;     /* amcmc_kernel_kind */
-  int32_t impl;            /* 0 = auto; 1 = thread-per-chain registers; 2 = block-per-chain smem; 3 = tcgen05 */
+  int32_t impl;            /* 0 = auto; 1 = thread-per-chain registers; 2 = block-per-chain smem; 3 = tcgen05
+                            * (DIAMONDS, fp32, ARWMH with adapt = 1: auto picks tcgen05 from 4096 chains) */
 } amcmc_run_args;
 
 /* ARWMH.init (arwmh.py:84-138).  If use_given_z == 0 draws q0 ~ U(-init_radius, init_radius)^d
