@@ -16,7 +16,7 @@
 namespace amcmc {
 
 constexpr int kBlockThreads = 256;       // many chains: several CTAs per SM
-constexpr int kBlockThreadsWide = 1024;  // few chains (at most one per SM): a wide CTA has 4x the loads in flight
+constexpr int kBlockThreadsWide = 512;   // few chains (at most one per SM): twice the loads in flight, still 128 registers per thread
 constexpr int kWideMaxChainsPerSm = 1;
 
 AMCMC_HD int colbase(int j, int d) { return j * (d - 1) - (j * (j - 1)) / 2; }

@@ -25,10 +25,11 @@ int launch_block_run(const BM& m, int d, const amcmc_state* st, const amcmc_run_
   const unsigned grid = (unsigned)st->n_chains;
   const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
   int rc = AMCMC_OK;
-  // Few chains (at most one per SM): one 1024-thread CTA per chain.  The likelihood phase is bound by the loads a CTA
-  // keeps in flight (diamonds: 21 k -> 12 k cycles per step, 14.9 -> 12.5 us per step at 64 chains); with two or more
-  // chains per SM the 256-thread CTAs win (296 chains: 16 us vs 25 us).  Staging half of the design matrix in the
-  // shared memory a wide CTA leaves unused was measured as well and changed nothing.
+  // Few chains (at most one per SM): one 512-thread CTA per chain.  The likelihood phase is bound by the loads a CTA
+  // keeps in flight; measured per step at 64 diamonds chains: 256 threads 14.9 us, 512 threads 10.4 us, 1024 threads
+  // 12.5 us (the 64-register cap slows the warp-0 sweep).  With two or more chains per SM the 256-thread CTAs win
+  // (200 chains: 15.8 us vs 20.3 us).  Staging half of the design matrix in the shared memory a wide CTA leaves unused
+  // was measured as well and changed nothing.
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -5,7 +5,7 @@ from adaptive_mcmc_b200 import models, _lib
 L = _lib.lib()
 data = models.synthetic_diamonds()
 names = ["loop top/collect", "draws+sync", "proposal matvec", "potential (likelihood)", "accept+mean+sync_and", "sweep+sync"]
-for C in (1, 64, 296, 512):
+for C in (64, 148, 200, 296, 400):
     s = am.ARWMH(models.diamonds, num_chains=C); s.impl = _lib.IMPL_BLOCK
     st = s.init(0, num_warmup=0, init_params=None, model_kwargs=data)
     b = am.ChainBatch.from_state(s.potential, st, copy=False)
