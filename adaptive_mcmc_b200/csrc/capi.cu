@@ -266,8 +266,13 @@ int amcmc_arwmh_run(const amcmc_model* m, amcmc_state* st, const amcmc_run_args*
     case AMCMC_MODEL_KIDIQ: rc = run_kidiq(m, st, a, s); break;
     case AMCMC_MODEL_DIAMONDS: {
       // many chains, fp32, per-chain adaptation: the likelihood goes to the tensor cores (impl 3 forces, impl 2 forbids)
+      // auto: the block kernel takes ~10 us per step with one chain per SM, 16 us with two and 31 us with three, the
+      // tensor-core kernel a constant ~21 us up to 128 chains per SM: it wins from two chains per SM upwards
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       const bool tc = a->adapt && a->kernel_kind == AMCMC_KERNEL_ARWMH && diamonds_tc_available(m) &&
-                      (a->impl == 3 || (a->impl == 0 && st->n_chains >= 4096));
+                      (a->impl == 3 || (a->impl == 0 && st->n_chains > (int64_t)2 * sms));
       if (a->impl == 3 && !tc) { set_error("amcmc_arwmh_run: tensor-core path unavailable (needs fp32, K = 25, adapt = 1)"); rc = AMCMC_ERR_UNSUPPORTED; break; }
       rc = tc ? run_diamonds_tc_adapt(m, st, a, s) : run_diamonds_block(m, st, a, s);
       break;

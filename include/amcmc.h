@@ -126,7 +126,7 @@ typedef struct amcmc_run_args {
   uint8_t* out_accept;     /* [n_steps][C] accept decisions, or NULL (parity tests) */
   int32_t kernel_kind;     /* amcmc_kernel_kind */
   int32_t impl;            /* 0 = auto; 1 = thread-per-chain registers; 2 = block-per-chain smem; 3 = tcgen05
-                            * (DIAMONDS, fp32, ARWMH with adapt = 1: auto picks tcgen05 from 4096 chains) */
+                            * (DIAMONDS, fp32, ARWMH with adapt = 1: auto picks tcgen05 above two chains per SM) */
 } amcmc_run_args;
 
 /* ARWMH.init (arwmh.py:84-138).  If use_given_z == 0 draws q0 ~ U(-init_radius, init_radius)^d
