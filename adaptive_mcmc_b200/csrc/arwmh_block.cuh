@@ -273,8 +273,9 @@ arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const 
     }
     if (a.out_acc && tid == 0) a.out_acc[t * C + c] = (uint8_t)acc;
     const int64_t n = (it < a.num_warmup) ? (it + 1) : (it + 1 - a.num_warmup);
+    // :185 running mean over n; the frozen kernel (sample_Pnx, pooled windows) reports the mean over THIS launch
     const R nf = (R)n;
-    macc = fma(alpha - macc, Num<R>::rcp(nf), macc);
+    macc = fma(alpha - macc, Num<R>::rcp(ADAPT ? nf : (R)(t + 1)), macc);
     if (ADAPT) {
       const bool n_is_one = (n == 1);
       const R gamma = n_is_one ? (R)1 : Num<R>::pow_neg(nf, a.lr_decay);
@@ -329,8 +330,9 @@ arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const 
       const int j = e2 - i * (i - 1) / 2;
       st.scale[(int64_t)tri_full(i, j) * C + c] = sm.Lt[cm_idx(i, j, d)] * sm.y[j];
     }
-    if (tid == 0) { st.lam[c] = lam; st.macc[c] = macc; st.asc[c] = asc; }
+    if (tid == 0) { st.lam[c] = lam; st.asc[c] = asc; }
   }
+  if (tid == 0) st.macc[c] = macc;
 }
 
 // ARWMH.init for block models: q0 (given or U(-r,r)), U0, loc = q0, scale = I, ...

@@ -203,6 +203,7 @@ AMCMC_HD void store_chain(const ChainRegs<R, D>& s, const StateView<R>& st, int6
 #pragma unroll
   for (int k = 0; k < D; ++k) st.z[k * C + c] = s.x[k];
   st.pe[c] = s.U;
+  st.macc[c] = s.macc;  // frozen kernel: mean acceptance probability over this launch (pooled windows read it)
   if (!ADAPT) return;
 #pragma unroll
   for (int k = 0; k < D; ++k) st.loc[k * C + c] = s.mu[k];
@@ -217,7 +218,6 @@ AMCMC_HD void store_chain(const ChainRegs<R, D>& s, const StateView<R>& st, int6
 #pragma unroll
     for (int j = 0; j < i; ++j) st.scale[tri_full(i, j) * C + c] = s.Lt[tri_strict(i, j)] * sd[j];
   st.lam[c] = s.lam;
-  st.macc[c] = s.macc;
   st.asc[c] = s.asc;
 }
 
@@ -244,7 +244,9 @@ AMCMC_HD void arwmh_chain_run(const Model& m, const StateView<R>& st, const RunV
     // :180-181  n restarts at 1 after warmup
     const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
     const bool last = (t == a.n_steps - 1);
-    const bool acc = arwmh_step<Model, R, ADAPT>(s, m, z, u, (R)n, n == 1, a.lr_decay, a.target, a.eps, last);
+    // frozen kernel (sample_Pnx, pooled windows): mean_accept_prob is the mean over THIS launch (the reference discards it)
+    const R nf = ADAPT ? (R)n : (R)(t + 1);
+    const bool acc = arwmh_step<Model, R, ADAPT>(s, m, z, u, nf, n == 1, a.lr_decay, a.target, a.eps, last);
     if (a.out_acc) a.out_acc[t * C + c] = (uint8_t)acc;
     if (--until_collect == 0) {
       until_collect = a.thinning;

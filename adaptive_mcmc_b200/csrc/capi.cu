@@ -353,6 +353,9 @@ int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args*
   const int64_t thin = ha->thinning;
   const int64_t S = (T > ha->collect_start) ? (T - ha->collect_start) / thin : 0;
   const bool ext = ha->rng_mode == AMCMC_RNG_EXTERNAL;
+  // external draws per step: ARWMH / RAM normals[d], uniforms[1]; ASSS normals[d + 1], uniforms[52] (include/amcmc.h)
+  const int64_t nrm_per_step = (ha->kernel_kind == AMCMC_KERNEL_ASSS) ? d + 1 : d;
+  const int64_t uni_per_step = (ha->kernel_kind == AMCMC_KERNEL_ASSS) ? 52 : 1;
   const bool want_z = ha->out_z && S > 0, want_pe = ha->out_potential_energy && S > 0;
   // chunking: ~2048 iterations per chunk, whole thinning periods, at most S samples
   int64_t chunk_S = (want_z || want_pe) ? ((2048 + thin - 1) / thin) : 0;
@@ -362,8 +365,8 @@ int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args*
   const size_t b_oz = want_z ? al((size_t)chunk_S * d * C * w) : 0;
   const size_t b_ope = want_pe ? al((size_t)chunk_S * C * w) : 0;
   const size_t b_acc = ha->out_accept ? al((size_t)T * C) : 0;
-  const size_t b_nrm = ext ? al((size_t)T * d * C * w) : 0;
-  const size_t b_uni = ext ? al((size_t)T * C * w) : 0;
+  const size_t b_nrm = ext ? al((size_t)T * nrm_per_step * C * w) : 0;
+  const size_t b_uni = ext ? al((size_t)T * uni_per_step * C * w) : 0;
   const size_t total = 4 * b_vec + 2 * b_mat + b_tri + 2 * (b_oz + b_ope) + b_acc + b_nrm + b_uni;
   if (m->scratch_bytes < total) {
     if (m->scratch) cudaFree(m->scratch);
@@ -402,8 +405,8 @@ int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args*
   H2D(ds.log_step_size, hst->log_step_size, (size_t)C * w);
   H2D(ds.as_change, hst->as_change, (size_t)C * w);
   if (ext) {
-    H2D(d_nrm, ha->normals, (size_t)T * d * C * w);
-    H2D(d_uni, ha->uniforms, (size_t)T * C * w);
+    H2D(d_nrm, ha->normals, (size_t)T * nrm_per_step * C * w);
+    H2D(d_uni, ha->uniforms, (size_t)T * uni_per_step * C * w);
   }
   int64_t t_done = 0, s_done = 0;
   int k = 0;
@@ -428,8 +431,8 @@ int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args*
     da.out_z = (want_z && ns) ? d_oz[buf] : nullptr;
     da.out_potential_energy = (want_pe && ns) ? d_ope[buf] : nullptr;
     da.out_accept = d_acc ? d_acc + (size_t)t_done * C : nullptr;
-    da.normals = ext ? (const void*)((const char*)d_nrm + (size_t)t_done * d * C * w) : nullptr;
-    da.uniforms = ext ? (const void*)((const char*)d_uni + (size_t)t_done * C * w) : nullptr;
+    da.normals = ext ? (const void*)((const char*)d_nrm + (size_t)t_done * nrm_per_step * C * w) : nullptr;
+    da.uniforms = ext ? (const void*)((const char*)d_uni + (size_t)t_done * uni_per_step * C * w) : nullptr;
     rc = amcmc_arwmh_run(m, &ds, &da, (void*)s0);
     if (rc) return rc;
     if (ns && (want_z || want_pe)) {

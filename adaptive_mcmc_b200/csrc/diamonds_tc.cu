@@ -448,9 +448,37 @@ int create_diamonds_tc(amcmc_model* m, const double* X, int64_t n, int K, const 
   return AMCMC_OK;
 }
 
+void tc_release_l2(DiamondsTcExtra* ex, bool wait) {
+  if (!ex->l2_dirty) return;
+  if (ex->have_done_ev) {
+    if (wait) cudaEventSynchronize(ex->done_ev);
+    else if (cudaEventQuery(ex->done_ev) != cudaSuccess) { cudaGetLastError(); return; }  // still running: try again later
+  }
+  cudaCtxResetPersistingL2Cache();
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ex->l2_prev_limit);
+  cudaGetLastError();
+  ex->l2_dirty = 0;
+}
+
+void tc_run_begin(DiamondsTcExtra* ex, cudaStream_t s) {
+  tc_release_l2(ex, false);
+  if (ex->have_done_ev && ex->last_stream != s) cudaStreamWaitEvent(s, ex->done_ev, 0);
+}
+
+void tc_run_end(DiamondsTcExtra* ex, cudaStream_t s) {
+  if (!ex->have_done_ev) {
+    if (cudaEventCreateWithFlags(&ex->done_ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return; }
+    ex->have_done_ev = 1;
+  }
+  cudaEventRecord(ex->done_ev, s);
+  ex->last_stream = s;
+}
+
 void destroy_diamonds_tc(amcmc_model* m) {
   DiamondsTcExtra* ex = (DiamondsTcExtra*)m->extra;
   if (!ex) return;
+  tc_release_l2(ex, true);
+  if (ex->have_done_ev) { cudaEventSynchronize(ex->done_ev); cudaEventDestroy(ex->done_ev); }
   if (ex->Xcanon) cudaFree(ex->Xcanon);
   if (ex->Xcanon64) cudaFree(ex->Xcanon64);
   if (ex->gram) cudaFree(ex->gram);
@@ -519,6 +547,7 @@ int run_diamonds_tc(const amcmc_model* m, const amcmc_state* st, const void* loc
   DiamondsTcExtra* ex = (DiamondsTcExtra*)m->extra;
   if (!ex) { set_error("diamonds tensor-core path needs K = 25 predictors and fp32"); return AMCMC_ERR_UNSUPPORTED; }
   TcParams p;
+  tc_run_begin(ex, s);
   int rc = diamonds_tc_prepare(m, st->n_chains, &p, st, a);
   if (rc) return rc;
   diamonds_tc_launch_ref(m, (const float*)loc, (const float*)scale_packed, (const float*)log_step, a->eps, s);
@@ -534,7 +563,9 @@ int run_diamonds_tc(const amcmc_model* m, const amcmc_state* st, const void* loc
     if ((rc = check_cuda(cudaFuncSetAttribute(diamonds_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::BYTES), "cudaFuncSetAttribute"))) return rc;
     diamonds_tc_kernel<false><<<grid, TC_THREADS, TcSmem::BYTES, s>>>(p);
   }
-  return check_cuda(cudaGetLastError(), "diamonds_tc_kernel launch");
+  rc = check_cuda(cudaGetLastError(), "diamonds_tc_kernel launch");
+  tc_run_end(ex, s);
+  return rc;
 }
 
 }  // namespace amcmc

@@ -50,7 +50,20 @@ struct DiamondsTcExtra {
   float* cref;       // [50][cref_cap] per-chain GEMM reference: rows 0-24 q_ref, rows 25-49 2 g
   double* crss;      // [cref_cap] RSS at the reference point
   int64_t cref_cap;
+  // The scratch above belongs to the model handle, so runs on one handle are serialised: a run on another stream waits
+  // for `done_ev` of the previous one (tc_run_begin / tc_run_end).  Host threads must not share a handle concurrently.
+  cudaEvent_t done_ev;
+  cudaStream_t last_stream;
+  int have_done_ev;
+  // persisting-L2 window of the adaptive path: released (cudaCtxResetPersistingL2Cache + previous limit restored) once
+  // the run that set it has finished -- checked at the next call on the handle and at amcmc_model_destroy
+  int l2_dirty;
+  size_t l2_prev_limit;
 };
+
+void tc_run_begin(DiamondsTcExtra* ex, cudaStream_t s);  // serialise against the previous run; release a finished L2 window
+void tc_run_end(DiamondsTcExtra* ex, cudaStream_t s);
+void tc_release_l2(DiamondsTcExtra* ex, bool wait);
 
 struct TcParams {
   int64_t C;

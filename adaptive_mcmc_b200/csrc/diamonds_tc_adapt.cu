@@ -640,6 +640,7 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
   DiamondsTcExtra* ex = (DiamondsTcExtra*)m->extra;
   if (!ex) { set_error("diamonds tensor-core path needs K = 25 predictors and fp32"); return AMCMC_ERR_UNSUPPORTED; }
   TcAdaptParams ap;
+  tc_run_begin(ex, s);
   int rc = diamonds_tc_prepare(m, st->n_chains, &ap.p, st, a);
   if (rc) return rc;
   ap.loc = (float*)st->loc;
@@ -717,7 +718,15 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     attr.accessPolicyWindow.hitRatio = 1.0f;
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (!pinned && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return; }
+    if (!pinned) {
+      if (!ex->l2_dirty) {  // remember the caller's limit; tc_release_l2 restores it once this run has finished
+        size_t prev = 0;
+        cudaDeviceGetLimit(&prev, cudaLimitPersistingL2CacheSize);
+        ex->l2_prev_limit = prev;
+      }
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return; }
+      ex->l2_dirty = 1;
+    }
     if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) pinned = true;
     else cudaGetLastError();  // pinning is an optimisation: run without it
   };
@@ -760,6 +769,7 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     attr.accessPolicyWindow.num_bytes = 0;
     cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
   }
+  tc_run_end(ex, s);  // the persisting lines themselves are released by tc_release_l2 when this event has completed
   return rc;
 }
 

@@ -110,8 +110,8 @@ __global__ void pooled_broadcast_kernel(int64_t C, int d, const R* __restrict__ 
   clam[c] = lam[0];
 }
 
-// NOTE: on the generic (CUDA-core) frozen path mean_accept_prob is the kernels' running mean over n = i+1, ...;
-// only the tensor-core path reports the mean over exactly this call.
+// Every frozen kernel (thread-per-chain, CTA-per-chain, tensor-core) reports mean_accept_prob as the mean acceptance
+// probability over exactly this call; amcmc_pooled_stats averages it over the chains for the Robbins-Monro step.
 
 bool diamonds_tc_available(const amcmc_model* m);
 int run_diamonds_tc(const amcmc_model* m, const amcmc_state* st, const void* loc, const void* scale_packed,

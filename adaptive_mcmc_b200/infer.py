@@ -24,8 +24,10 @@ _CHEAP = {"potential_energy", "z"}
 class MCMC:
     def __init__(self, sampler, *, num_warmup, num_samples, num_chains=1, thinning=1, progress_bar=False,
                  chain_method="vectorized", **unused):
-        if num_samples % thinning != 0 and num_samples < thinning:
-            raise ValueError("num_samples must be >= thinning")
+        if int(thinning) < 1 or int(num_warmup) < 0:
+            raise ValueError("thinning must be >= 1 and num_warmup >= 0")
+        if int(num_samples) < int(thinning):
+            raise ValueError("num_samples must be >= thinning (at least one kept sample)")
         self.sampler = sampler
         self.num_warmup = int(num_warmup)
         self.num_samples = int(num_samples)
@@ -86,7 +88,10 @@ class MCMC:
                 if f == "potential_energy":
                     extras[f] = torch.stack(pes, dim=1)
                 elif f == "adapt_state":
-                    extras[f] = ARWMHAdaptState(torch.stack(locs, 1), torch.stack(scales, 1), torch.stack(lams, 1))
+                    if getattr(s, "_adapt_has_step_size", True):
+                        extras[f] = ARWMHAdaptState(torch.stack(locs, 1), torch.stack(scales, 1), torch.stack(lams, 1))
+                    else:  # ASSS: (loc, scale) only, the sampler's own record type (asss.py:28)
+                        extras[f] = s._adapt_record(torch.stack(locs, 1), torch.stack(scales, 1))
                 elif f == "mean_accept_prob":
                     extras[f] = torch.stack(maccs, dim=1)
                 elif f == "as_change":

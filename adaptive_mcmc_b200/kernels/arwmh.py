@@ -429,9 +429,41 @@ class ARWMH:
         batch.lam.fill_(float(lss))
         batch.macc.zero_()
         batch.asc.zero_()
-        self.run_batch(batch, int(n), collect=(), adapt=False)
+        if not self._run_frozen_shared(batch, loc, scale, lss, int(n)):
+            self.run_batch(batch, int(n), collect=(), adapt=False)
         out = batch.z.t().reshape(P, int(n_samples), pot.dim)
         return pot.unravel(out) if is_dict else out
+
+    def _run_frozen_shared(self, batch, loc, dense_scale, lss, n):
+        """Frozen steps with ONE adaptation state for all chains (what sample_Pnx is): for many fp32 diamonds chains
+        this is the tcgen05 shared-state kernel (amcmc_pooled_run -> diamonds_tc_kernel) instead of one CTA per chain.
+        Returns False when that path does not apply (the caller then uses the per-chain frozen kernels)."""
+        pot = batch.potential
+        sms = torch.cuda.get_device_properties(pot.device).multi_processor_count
+        if not (pot.family.name == "diamonds" and pot.dtype == torch.float32 and pot.dim == 26
+                and batch.C > 2 * sms and self.impl in (_lib.IMPL_AUTO, _lib.IMPL_TENSOR)):
+            return False
+        d = pot.dim
+        ii, jj = torch.tril_indices(d, d, device=pot.device)
+        packed = dense_scale[ii, jj].contiguous()
+        loc = loc.contiguous()
+        lam = lss.reshape(1).contiguous()
+        pool = _lib.AmcmcPooled()
+        pool.dim, pool.dtype = d, _lib.AMCMC_F32
+        pool.loc, pool.scale, pool.log_step_size = loc.data_ptr(), packed.data_ptr(), lam.data_ptr()
+        pool.cov, pool.window = 0, 0
+        a = _lib.AmcmcRunArgs()
+        a.n_steps, a.thinning, a.collect_start, a.num_warmup = n, 1, n, 0
+        a.lr_decay, a.target_accept_prob, a.eps = self._lr_decay, self._target_accept_prob, self._eps
+        a.adapt, a.seed, a.chain_offset, a.impl = 0, batch.seed, batch.chain_offset, _lib.IMPL_TENSOR
+        a.rng_mode = _lib.RNG_PHILOX
+        st = batch.cstruct()
+        with torch.cuda.device(pot.device):
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().amcmc_pooled_run(pot.handle, C.byref(st), C.byref(pool), C.byref(a), stream),
+                       "amcmc_pooled_run")
+        batch.i = int(st.i)
+        return True
 
     def get_init_adapt_state(self, rng_key, init_params, model_args=(), model_kwargs={}):
         """Return the first adapt state after initialization (arwmh.py:272-276)."""

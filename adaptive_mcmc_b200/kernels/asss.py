@@ -37,6 +37,8 @@ class ASSS(ARWMH):
     """
 
     sample_field = "z"
+    _adapt_has_step_size = False      # MCMC(extra_fields=("adapt_state",)) returns ASSSAdaptState records
+    _adapt_record = ASSSAdaptState
 
     def __init__(self, model=None, potential_fn=None, lr_decay=2 / 3, eps=1e-6, init_strategy=init_to_uniform, *,
                  num_chains=1, dtype=torch.float32, device=None, chain_offset=0):

@@ -1,0 +1,186 @@
+"""GPU tests added in round 2 for the paths the round-1 review found untested:
+
+* `amcmc_arwmh_run_host` with ASSS + external draws (normals[T][d+1][C], uniforms[T][52][C]);
+* the register kernel's frozen template (`adapt = 0`, ARWMH.sample_Pnx, arwmh.py:230-249) against the oracle on shared draws;
+* pooled adaptation on the generic CUDA-core paths (thread-per-chain and CTA-per-chain): the window's mean acceptance
+  probability must reach the Robbins-Monro update, so the shared step size converges to the 0.234 target;
+* frozen many-chain diamonds `sample_Pnx` runs on the tensor-core shared-state kernel and agrees with the block kernel.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import adaptive_mcmc_b200 as am
+from adaptive_mcmc_b200 import _lib, models
+from adaptive_mcmc_b200.parallel import PooledARWMH
+from oracle import arwmh_numpy as o
+from oracle import c_oracle as co
+from oracle import pooled_numpy as op
+
+pytestmark = pytest.mark.gpu
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _host_state(batch, host):
+    hs = _lib.AmcmcState()
+    hs.n_chains, hs.dim, hs.dtype, hs.i = batch.C, batch.d, (0 if batch.z.dtype == torch.float32 else 1), batch.i
+    hs.z, hs.potential_energy, hs.mean_accept_prob = host["z"].data_ptr(), host["pe"].data_ptr(), host["macc"].data_ptr()
+    hs.loc, hs.scale, hs.log_step_size = host["loc"].data_ptr(), host["scale"].data_ptr(), host["lam"].data_ptr()
+    hs.as_change = host["asc"].data_ptr()
+    return hs
+
+
+@pytest.mark.parametrize("T", [7, 3000])  # 3000 > one 2048-step chunk of the host entry: the chunk offsets matter
+def test_run_host_asss_external_draws(T):
+    """The host-buffer entry point must size and offset the external draws by the sampler kind: ASSS reads
+    normals[T][d+1][C] and uniforms[T][52][C] (include/amcmc.h).  Bit-identical to the device-pointer path."""
+    Cn, d = 96, 10
+    s = am.ASSS(models.eight_schools, num_chains=Cn)
+    st = s.init(2, num_warmup=0, init_params=None)
+    b = s._batch_from_state(st)
+    host = {f: getattr(b, f).cpu().pin_memory() for f in b._FIELDS}
+    g = torch.Generator().manual_seed(5)
+    nrm = torch.randn(T, Cn, d + 1, generator=g)
+    uni = torch.rand(T, Cn, 52, generator=g)
+    dn, du = s._draws_to_device_layout((nrm, uni))  # [T][d+1][C], [T][52][C]
+    raw = s.run_batch(b, T, thinning=5, draws=(dn, du))
+    hn, hu = dn.cpu().contiguous().pin_memory(), du.cpu().contiguous().pin_memory()
+    hs = _host_state(b, host)
+    hs.i = 0
+    a = _lib.AmcmcRunArgs()
+    a.n_steps, a.thinning, a.collect_start, a.num_warmup = T, 5, 0, 0
+    a.lr_decay, a.target_accept_prob, a.eps = 2 / 3, 0.234, 1e-6
+    a.adapt, a.rng_mode, a.seed, a.kernel_kind = 1, _lib.RNG_EXTERNAL, 2, _lib.KERNEL_ASSS
+    a.normals, a.uniforms = hn.data_ptr(), hu.data_ptr()
+    S = T // 5
+    oz = torch.empty(S, d, Cn).pin_memory()
+    ope = torch.empty(S, Cn).pin_memory()
+    a.out_z, a.out_potential_energy = oz.data_ptr(), ope.data_ptr()
+    _lib.check(_lib.lib().amcmc_arwmh_run_host(s.potential.handle, C.byref(hs), C.byref(a)), "run_host")
+    assert hs.i == T
+    torch.testing.assert_close(oz, raw["z"].cpu(), rtol=0, atol=0)
+    torch.testing.assert_close(ope, raw["potential_energy"].cpu(), rtol=0, atol=0)
+    torch.testing.assert_close(host["scale"], b.scale.cpu(), rtol=0, atol=0)
+    torch.testing.assert_close(host["z"], b.z.cpu(), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_frozen_register_kernel_matches_oracle(prec):
+    """the `ADAPT = false` template of the thread-per-chain kernel (what ARWMH.sample_Pnx launches) on
+    shared draws against the oracle's frozen step (arwmh.py:230-249): identical decisions, positions within tolerance,
+    the adaptation state bit-for-bit untouched, mean_accept_prob = mean acceptance probability over the launch."""
+    tdt, ndt, tol = (torch.float64, np.float64, 1e-9) if prec == "f64" else (torch.float32, np.float32, 1e-3)
+    Cn, d, T = 512, 10, 120
+    rng = np.random.default_rng(17)
+    s = am.ARWMH(models.eight_schools, num_chains=Cn, dtype=tdt)
+    st = s.init(8, num_warmup=0, init_params=None)
+    b = am.ChainBatch.from_state(s.potential, st)
+    scale0 = np.tril(rng.normal(size=(d, d)) * 0.15 + np.eye(d) * 0.6)
+    b.set_dense_scale(torch.from_numpy(scale0))
+    b.lam.fill_(-0.4)
+    loc0, sc0, lam0 = b.loc.clone(), b.scale.clone(), b.lam.clone()
+    nrm = rng.normal(size=(T, Cn, d)).astype(ndt)
+    uni = rng.random(size=(T, Cn)).astype(ndt)
+    dr = s._draws_to_device_layout((torch.from_numpy(nrm), torch.from_numpy(uni)))
+    z0 = _np(b.z.t()).astype(ndt)
+    raw = s.run_batch(b, T, draws=dr, adapt=False, record_accept=True)
+    assert torch.equal(b.loc, loc0) and torch.equal(b.scale, sc0) and torch.equal(b.lam, lam0)
+    pot = o.make_potential("eight_schools")
+    ost = o.arwmh_init(pot, z0)
+    ost = ost._replace(adapt_state=o.ARWMHAdaptState(z0.copy(), np.broadcast_to(scale0.astype(ndt), (Cn, d, d)).copy(),
+                                                     np.full(Cn, -0.4, ndt)))
+    alphas, accs, zs = [], [], []
+    for t in range(T):
+        ost, alpha, acc = o.arwmh_step(ost, pot, nrm[t], uni[t], adapt=False)
+        alphas.append(alpha); accs.append(acc); zs.append(ost.z.copy())
+    accs, zs = np.stack(accs), np.stack(zs)
+    same = (_np(raw["accept"]).astype(bool) == accs).all(axis=0)
+    assert same.mean() >= (1.0 if prec == "f64" else 0.95), same.mean()
+    zg = _np(raw["z"]).transpose(0, 2, 1)
+    err = (np.abs(zg - zs) / (1 + np.abs(zs))).max(axis=(0, 2))[same]
+    assert err.max() < (tol if prec == "f64" else 10 * tol) and np.quantile(err, 0.99) < tol
+    np.testing.assert_allclose(_np(b.macc)[same], np.stack(alphas).mean(0)[same], rtol=1e-4, atol=1e-5)
+
+
+def test_pooled_generic_thread_per_chain_matches_oracle_and_adapts():
+    """Pooled adaptation on the thread-per-chain kernel (eight_schools): (i) three windows against the float64 pooled
+    oracle on shared draws -- the shared log step size only matches if the window's acceptance rate reaches the update;
+    (ii) a long Philox run settles at the 0.234 target."""
+    Cn, d, K = 256, 10, 20
+    rng = np.random.default_rng(3)
+    s = PooledARWMH(models.eight_schools, num_chains=Cn, pool_every=K, dtype=torch.float64)
+    s.init(11)
+    z = _np(s.batch.z.t()).copy()
+    pot = o.make_potential("eight_schools")
+    U = pot(z)
+    pool = op.pooled_init(z)
+    for w in range(3):
+        nrm, uni = rng.normal(size=(K, Cn, d)), rng.random(size=(K, Cn))
+        dn = torch.from_numpy(nrm).permute(0, 2, 1).contiguous()
+        s.run_window(K, collect=(), draws=(dn, torch.from_numpy(uni)))
+        z, U, pool, info = op.pooled_window(pot, z, U, pool, K, w * K, draws=(nrm, uni))
+        np.testing.assert_allclose(_np(s.batch.macc), info["mean_accept"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(_np(s.batch.z.t()), z, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(float(s.log_step_size), pool["lam"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(_np(s.loc), pool["loc"], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(_np(s.dense_scale()), pool["L"], rtol=1e-8, atol=1e-10)
+    s = PooledARWMH(models.eight_schools, num_chains=4096, pool_every=50)
+    s.init(12)
+    s.run(50 * 400, thinning=50, collect=())
+    accs = []
+    for _ in range(20):
+        s.run_window(50, collect=())
+        accs.append(float(s.batch.macc.mean()))
+    assert abs(np.mean(accs) - 0.234) < 0.03, np.mean(accs)
+    assert -3.0 < float(s.log_step_size) < 1.0
+
+
+def test_pooled_generic_block_kernel_adapts_on_diamonds():
+    """The same through the CTA-per-chain kernel (impl = block): before the fix the frozen kernel never stored its
+    acceptance rate and the shared step size shrank monotonically."""
+    data = models.synthetic_diamonds(n=5000, k=25, seed=0)
+    X, Y = data["X"], data["Y"]
+    Xc = np.column_stack([np.ones(len(Y)), X[:, 1:] - X[:, 1:].mean(0)])
+    mode = np.concatenate([np.linalg.lstsq(Xc, Y, rcond=None)[0], [np.log(0.123)]])
+    Cn, d = 512, 26
+    q0 = mode[None] + 0.01 * np.random.default_rng(6).normal(size=(Cn, d))
+    s = PooledARWMH(models.diamonds, num_chains=Cn, pool_every=50, init_strategy=am.init_to_value(torch.from_numpy(q0)),
+                    impl=_lib.IMPL_BLOCK)
+    s.init(9, model_kwargs=data)
+    s.scale.mul_(0.01)
+    s.cov.mul_(1e-4)
+    s.run(50 * 80, thinning=50, collect=())
+    accs = []
+    for _ in range(10):
+        s.run_window(50, collect=())
+        accs.append(float(s.batch.macc.mean()))
+    assert abs(np.mean(accs) - 0.234) < 0.06, np.mean(accs)
+
+
+def test_sample_Pnx_diamonds_runs_on_tensor_cores():
+    """ADVICE (round 1): frozen many-chain diamonds sample_Pnx must reach the tcgen05 shared-state kernel, not one CTA per
+    chain.  Same Philox streams through both implementations: identical decisions for almost every chain."""
+    data = models.synthetic_diamonds(n=5000, k=25, seed=0)
+    X, Y = data["X"], data["Y"]
+    Xc = np.column_stack([np.ones(len(Y)), X[:, 1:] - X[:, 1:].mean(0)])
+    mode = np.concatenate([np.linalg.lstsq(Xc, Y, rcond=None)[0], [np.log(0.123)]])
+    d = 26
+    pts = torch.from_numpy(mode[None] + 0.003 * np.random.default_rng(1).normal(size=(8, d))).float()
+    ast = am.ARWMHAdaptState(torch.from_numpy(mode).float(), torch.eye(d) * 0.002, torch.tensor(0.0))
+    outs = {}
+    for impl in (_lib.IMPL_AUTO, _lib.IMPL_BLOCK):
+        s = am.ARWMH(models.diamonds)
+        s.init(0, 0, None, model_kwargs=data)
+        s.impl = impl
+        outs[impl] = s.sample_Pnx(21, pts, ast, n=8, n_samples=256)  # 2048 chains > 2 per SM
+    a, b = outs[_lib.IMPL_AUTO], outs[_lib.IMPL_BLOCK]
+    assert a.shape == (8, 256, d)
+    moved = (a - pts[:, None].to(a.device)).abs().amax(-1) > 0
+    assert 0.3 < float(moved.float().mean()) <= 1.0
+    close = ((a - b).abs().amax(-1) < 2e-5).float().mean()
+    assert float(close) > 0.95, float(close)

@@ -88,3 +88,12 @@ def test_save_states_in_reference_pickle_format(tmp_path):
     assert got.potential_energy.shape == (S,) and got.adapt_state.scale.shape == (S, d, d) and got.z["theta"].shape == (S, 2)
     np.testing.assert_array_equal(got.potential_energy, st.potential_energy[:, 1].numpy())
     np.testing.assert_array_equal(got.i, np.arange(1, S + 1))
+
+
+def test_mcmc_ctor_validation():
+    """numpyro.infer.MCMC needs at least one kept sample; thinning >= 1 (num_samples = 0 slipped through)."""
+    for bad in (dict(num_warmup=0, num_samples=0), dict(num_warmup=0, num_samples=5, thinning=10),
+                dict(num_warmup=0, num_samples=10, thinning=0), dict(num_warmup=-1, num_samples=10)):
+        with pytest.raises(ValueError):
+            am.MCMC(None, **bad)
+    am.MCMC(None, num_warmup=0, num_samples=10, thinning=10)
