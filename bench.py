@@ -46,6 +46,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-extra", action="store_true", help="skip the secondary diamonds tensor-core workload")
+    p.add_argument("--probe-d2h", action="store_true",
+                   help="only measure pinned device->host / host->device copy bandwidth of every rank, alone and concurrently")
     return p.parse_args()
 
 
@@ -68,26 +70,72 @@ def cpu_oracle_rate(workload, dtype, chains, mcmc_steps, repeats=1, n_threads=0)
     return chains * mcmc_steps / best, best
 
 
+REF_ITERS_PER_STEP = 200  # reference arm: fused iterations per bench step (bounded sample, same chain count as ours)
+
+
+def _ess_of(kept, chains_total):
+    """NumPyro-definition ESS (oracle restatement) of kept draws [S, C', d], scaled from C' to all chains."""
+    import numpy as np
+    from oracle import arwmh_numpy as onp
+
+    x = np.ascontiguousarray(np.transpose(kept, (1, 0, 2)), np.float64)  # [C', S, d]
+    ess = onp.effective_sample_size(x)
+    return float(np.min(ess)) * (chains_total / x.shape[0])
+
+
 def run_reference(args):
+    """CPU arm.  Order of preference: (1) the UNMODIFIED reference (JAX + NumPyro, `numpyro.infer.MCMC(ARWMH(model),
+    num_chains=C, chain_method="vectorized")`) when `import jax, numpyro` works here or from baseline/_ref
+    (scripts/jax_bridge.py); (2) the C restatement oracle/arwmh_oracle.c on all host cores.  Same workload, chain count,
+    thinning and metric as our arm; each bench step is a bounded sample (REF_ITERS_PER_STEP fused iterations)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    chains, T = 4096, 2000  # bounded sample: ~2 s of CPU work per bench step on 8 cores
+    wl = WORKLOADS[args.workload]
+    chains = args.chains or wl["chains"]
+    T = REF_ITERS_PER_STEP
     import numpy as np
-    from oracle import arwmh_numpy as onp, c_oracle
 
-    ndt = np.float32 if args.dtype == "f32" else np.float64
-    q0 = c_oracle.init_uniform(0, chains, 10, dt=ndt)
-    st = onp.arwmh_init(onp.make_potential("eight_schools"), q0)
-    for _ in range(max(args.warmup, 1)):
-        st, _ = c_oracle.arwmh_run(st, "eight_schools", T, seed=0, thinning=args.thinning, n_threads=cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        st, _ = c_oracle.arwmh_run(st, "eight_schools", T, seed=0, thinning=args.thinning, n_threads=cores)
-    el = time.perf_counter() - t0
-    val = chains * T * args.steps / el
-    sample = f"{chains} chains x {T} fused iterations per step (C oracle port, OpenMP over chains)"
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import jax_bridge
+
+    jax_ok, jax_detail = jax_bridge.probe()
+    ref_root = jax_bridge.find_reference()
+    kind, note, val, el, min_ess = "port", "", None, None, None
+    if jax_ok and ref_root:
+        try:  # the real thing: warm-up steps untimed (also compiles), then K timed steps as one MCMC.run
+            rate, sec, mcmc = jax_bridge.time_reference(ref_root, chains, T * args.steps, args.thinning,
+                                                        T * max(args.warmup, 1))
+            val, el, kind = rate, sec, "reference"
+            zs = mcmc.get_samples(group_by_chain=True)
+            flat = np.concatenate([np.asarray(v).reshape(v.shape[0], v.shape[1], -1) for k, v in sorted(zs.items())
+                                   if k != "theta"], axis=-1)  # [C, S, d]; tau is constrained here (monotone map: same ESS)
+            min_ess = _ess_of(np.transpose(flat[:4096], (1, 0, 2)), chains)
+            note = f"unmodified reference through numpyro.infer.MCMC ({jax_detail}), JIT compile excluded"
+        except Exception as e:  # fall back to the port, and say why
+            note = f"jax present ({jax_detail}) but the reference run failed: {repr(e)[:200]}; "
+    if val is None:
+        from oracle import arwmh_numpy as onp, c_oracle
+
+        ndt = np.float32 if args.dtype == "f32" else np.float64
+        q0 = c_oracle.init_uniform(0, chains, 10, dt=ndt)
+        st = onp.arwmh_init(onp.make_potential("eight_schools"), q0)
+        nw = T * max(args.warmup, 1)
+        for _ in range(max(args.warmup, 1)):
+            st, _ = c_oracle.arwmh_run(st, "eight_schools", T, seed=0, thinning=args.thinning, n_threads=cores, num_warmup=nw)
+        kept = []
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st, coll = c_oracle.arwmh_run(st, "eight_schools", T, seed=0, thinning=args.thinning, n_threads=cores, num_warmup=nw)
+            kept.append(coll["z"][:, :4096])
+        el = time.perf_counter() - t0
+        val = chains * T * args.steps / el
+        min_ess = _ess_of(np.concatenate(kept, 0), chains)
+        note += (f"reference = JAX/NumPyro, not importable here ({jax_detail}); timed arm is the C restatement "
+                 "oracle/arwmh_oracle.c (OpenMP over chains)")
+    sample = (f"{chains} chains x {T} fused iterations per step, thinning {args.thinning}; the chains are in iterations "
+              f"{T * max(args.warmup, 1)}..{T * (max(args.warmup, 1) + args.steps)} of their adaptation (ours: 10,000 per step)")
     line = {
         "impl": "reference",
         "metric": "chain-steps/sec",
@@ -102,10 +150,13 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": args.dtype,
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload]["label"], "sample": sample, "thinning": args.thinning},
-        "cpu_baseline": {"value": val, "unit": "chain-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": wl["label"], "chains_per_gpu": chains, "fused_iterations_per_step": T,
+                   "thinning": args.thinning, "sample": sample},
+        "min_ess_per_sec": min_ess / el,
+        "cpu_baseline": {"value": val, "unit": "chain-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference = JAX/NumPyro (not installable offline); timed arm is the C restatement oracle/arwmh_oracle.c",
+        "jax_probe": {"available": jax_ok, "detail": jax_detail, "reference_checkout": bool(ref_root)},
+        "note": note,
     }
     print(json.dumps(line))
 
@@ -185,6 +236,13 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.probe_d2h:
+        res = probe_copies(dev, world, local, quick=False)
+        if rank == 0:
+            print(json.dumps({"probe": "pinned host <-> device copies", "n_gpus": world, **res}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload in ("diamonds", "gaussian_ram"):  # secondary workload on its own (profiling, scaling runs)
         K, W = args.steps, max(args.warmup, 3)
         res = (run_diamonds_tc if args.workload == "diamonds" else run_gaussian_ram)(args, world, rank, dev, K, W)
@@ -305,6 +363,8 @@ def run_ours(args):
             "h2d_bytes_per_step": state_bytes,
             "d2h_bytes_per_step": state_bytes + S * (d + 1) * Cn * esz,
             "api": "amcmc_arwmh_run_host (C ABI, pinned host buffers)",
+            "d2h_GBps_per_rank": (state_bytes + S * (d + 1) * Cn * esz) * K / float(te.item()) / 1e9,
+            "copy_probe": probe_copies(dev, world, local, quick=True),
         }
         S_ = T // args.thinning
         chunk_S = min(S_, (2048 + args.thinning - 1) // args.thinning) or 1
@@ -336,7 +396,8 @@ def run_ours(args):
         extra = {}
         for name, fn in (("diamonds_tc", run_diamonds_tc), ("diamonds_tc_adaptive", run_diamonds_adaptive),
                          ("gaussian_ram", run_gaussian_ram), ("asss_eight_schools", run_asss),
-                         ("sample_Pnx_std_normal", run_sample_pnx)):
+                         ("sample_Pnx_std_normal", run_sample_pnx), ("configs0_eight_schools_4x10k", run_config0),
+                         ("configs1_diamonds_64x50k", run_config1), ("pooled_multi_rank_check", run_pooled_check)):
             try:
                 extra[name] = fn(args, world, rank, dev, max(3, K // 2), 2)
             except Exception as e:  # the headline line must survive a failure of a secondary workload
@@ -403,13 +464,19 @@ def run_ours(args):
                      "peak = fallback 6650 GB/s (of fallback)"),
         },
     }
+    # The state stays in registers for all fused iterations, so the HBM figure above is the SURVEY 8(d) "state-equivalent"
+    # number (it exceeds 1 by design) and NOT a utilisation.  What binds the kernel is instruction issue: thread
+    # instructions per chain-step from the committed ncu capture (profiles/instr.json) x chain-steps/s / 32 lanes against
+    # 4 schedulers x SMs x the SM clock sampled during the timed region.
+    line["roofline"]["binding"] = "issue -- see roofline_issue; frac > 1 here means the state round trip was removed, not 'over peak'"
+    line["roofline_issue"] = _issue_roofline(f"{args.workload}_{args.dtype}", value / world, clk, dev)
     if thin1 is not None:
         line["thinning_1"] = thin1
     if extra is not None:
         line["extra_workloads"] = extra
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        cc, ct = 4096, 5000
+        cc, ct = Cn, 2000  # same chain count as the GPU arm, a bounded number of iterations (~10-20 s of CPU work)
         rate, el = cpu_oracle_rate(args.workload, args.dtype, cc, ct, repeats=1, n_threads=cores)
         line["cpu_baseline"] = {
             "value": rate, "unit": "chain-steps/s", "cores": cores, "kind": "port",
@@ -634,7 +701,9 @@ def run_gaussian_ram(args, world, rank, dev, K, W):
                     "(BASELINE.json configs[4]); inputs (1.3 GB of state) exceed L2",
         "metric": "chain-steps/sec", "value": rate, "unit": "chain-steps/s", "ms_per_step": ms / K,
         "fused_iterations_per_step": T, "mean_accept_prob": float(b.macc.mean()), "gpu_launches": K,
+        "roofline_issue": _issue_roofline("gaussian_ram_f32", rate / world, None, dev),
         "roofline": {"bound": "hbm", "unit": "GB/s", "peak": hbm, "achieved": achieved, "frac": achieved / hbm,
+                     "binding": "issue / shared-memory port -- see roofline_issue (the factor is SMEM-resident for all fused steps)",
                      "traffic": _traffic(f"gaussian_ram_T{T}"),
                      "note": "algorithmic bytes = 2*4*(d(d+1)/2+2d+3) = 164,024 per chain-step (state round trip, SURVEY 8d); the "
                              "factor stays in shared memory for all fused steps of a launch, so real HBM traffic is ~1/400 of that"},
@@ -710,6 +779,206 @@ def run_sample_pnx(args, world, rank, dev, K, W):
             "metric": "chain-steps/sec", "value": world * 100 * 100_000 * 5 * K / el, "unit": "chain-steps/s", "ms_per_step": 1e3 * el / K,
             "timing": "host wall clock around the whole API call", "reference_recorded": {"seconds_per_call": 2.28, "chain_steps_per_s": 2.2e7,
             "hardware": "laptop CPU, JAX vmap (SURVEY section 6)"}, "last_mean": m, "gpu_launches": K * 3}
+
+
+# ------------------------------------------------------------------------------------------------
+# host <-> device copy ceiling of the box (explains the end-to-end scaling: every rank streams its thinned samples
+# to pinned host memory, all ranks into the same host)
+# ------------------------------------------------------------------------------------------------
+def probe_copies(dev, world, local, quick=True):
+    """Pinned D2H / H2D bandwidth of this rank alone (ranks take turns) and of all ranks at once.  GB/s per rank."""
+    import torch
+    import torch.distributed as dist
+
+    nbytes = (256 if quick else 1024) << 20
+    reps = 3 if quick else 8
+    hbuf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dbuf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    d2h = lambda: hbuf.copy_(dbuf, non_blocking=True)
+    h2d = lambda: dbuf.copy_(hbuf, non_blocking=True)
+    out = {}
+    alone = torch.zeros(world, 2, dtype=torch.float64, device=dev)
+    rank = dist.get_rank() if world > 1 else 0
+    for r in range(world):  # one rank at a time
+        if world > 1:
+            dist.barrier()
+        if r == rank:
+            alone[r, 0], alone[r, 1] = timed(d2h), timed(h2d)
+    if world > 1:
+        dist.all_reduce(alone)
+        dist.barrier()
+    both = torch.zeros(world, 2, dtype=torch.float64, device=dev)
+    both[rank, 0] = timed(d2h)  # all ranks concurrently
+    if world > 1:
+        dist.barrier()
+    both[rank, 1] = timed(h2d)
+    if world > 1:
+        dist.all_reduce(both)
+    out["d2h_GBps_alone"] = [round(float(v), 2) for v in alone[:, 0]]
+    out["h2d_GBps_alone"] = [round(float(v), 2) for v in alone[:, 1]]
+    out["d2h_GBps_concurrent"] = [round(float(v), 2) for v in both[:, 0]]
+    out["h2d_GBps_concurrent"] = [round(float(v), 2) for v in both[:, 1]]
+    out["bytes_per_copy"] = nbytes
+    try:
+        out["numa_nodes"] = len([n for n in os.listdir("/sys/devices/system/node") if n.startswith("node")])
+    except OSError:
+        out["numa_nodes"] = None
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0] and configs[1]: the reference-style runs through the MCMC driver, CPU port beside them
+# ------------------------------------------------------------------------------------------------
+def _wall(fn, dev):
+    import torch
+
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize(dev)
+    return out, time.perf_counter() - t0
+
+
+def run_config0(args, world, rank, dev, K, W):
+    """configs[0]: eight_schools, 4 chains x 10k steps (+1k warm-up), the reference's own CPU-runnable case, through
+    MCMC(ARWMH(model)).run like python/scripts/run_eight_schools_wasserstein.py:48-52.  Latency-bound on a GPU (4 threads)."""
+    import numpy as np
+    import torch
+
+    import adaptive_mcmc_b200 as am
+    from oracle import arwmh_numpy as onp, c_oracle
+
+    def once(seed):
+        mcmc = am.MCMC(am.ARWMH(am.models.eight_schools, device=dev, chain_offset=rank * 4), num_warmup=1000, num_samples=10000, num_chains=4)
+        mcmc.run(seed, extra_fields=("potential_energy",))
+        return mcmc
+
+    once(0)
+    times = []
+    for k in range(max(K, 3)):
+        mcmc, el = _wall(lambda: once(k + 1), dev)
+        times.append(el)
+    el = float(np.median(times))
+    smp = mcmc.get_samples(group_by_chain=True)
+    res = {"workload": "eight_schools-eight_schools_centered (d=10), adaptive Metropolis, 4 chains x (1k warm-up + 10k) steps per GPU "
+                       "(BASELINE.json configs[0]) through MCMC(ARWMH(model)).run", "metric": "chain-steps/sec",
+           "value": world * 4 * 11000 / el, "unit": "chain-steps/s", "wall_s": el, "timing": "host wall clock around mcmc.run (init + one fused launch + postprocess)",
+           "mu_mean": float(smp["mu"].mean()), "tau_mean": float(smp["tau"].mean()), "gpu_launches": 2 * max(K, 3),
+           "reference_recorded": {"chain_steps_per_s": 5.6e4, "hardware": "laptop CPU, 1 chain (SURVEY section 6)"}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        q0 = c_oracle.init_uniform(0, 4, 10, dt=np.float32)
+        st = onp.arwmh_init(onp.make_potential("eight_schools"), q0)
+        t0 = time.perf_counter()
+        c_oracle.arwmh_run(st, "eight_schools", 11000, seed=0, n_threads=4, num_warmup=1000)
+        ct = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 4 * 11000 / ct, "unit": "chain-steps/s", "cores": 4, "kind": "port",
+                               "sample": f"the same 4 chains x 11,000 steps, C oracle, {ct * 1e3:.1f} ms"}
+    return res
+
+
+def run_config1(args, world, rank, dev, K, W):
+    """configs[1]: diamonds (d=26, N=5000), 64 chains x 50k steps from the reference's own start (U(-2,2), identity
+    factor) through the MCMC driver; 64 chains = one CTA per chain on the block kernel.  From that start the chains have
+    NOT converged after 50k steps (the reference's diamonds runs use a 10^6-step warm-up, run_diamonds_wasserstein.py:67):
+    `last_U` is reported next to the time so that nobody reads the run as a converged posterior sample."""
+    import numpy as np
+    import torch
+
+    import adaptive_mcmc_b200 as am
+    from oracle import arwmh_numpy as onp, c_oracle
+
+    data = am.models.synthetic_diamonds(n=5000, k=25, seed=0)
+
+    def once(seed):
+        mcmc = am.MCMC(am.ARWMH(am.models.diamonds, device=dev, chain_offset=rank * 64), num_warmup=0, num_samples=50000, thinning=50, num_chains=64)
+        mcmc.run(seed, **data, extra_fields=("potential_energy",))
+        return mcmc
+
+    once(0)
+    mcmc, el = _wall(lambda: once(1), dev)
+    pe = mcmc.get_extra_fields(group_by_chain=True)["potential_energy"]
+    res = {"workload": "diamonds-diamonds synthetic (d=26, N=5000), adaptive Metropolis, 64 chains x 50k steps per GPU (BASELINE.json "
+                       "configs[1]) through MCMC(ARWMH(model)).run, CTA-per-chain block kernel", "metric": "chain-steps/sec",
+           "value": world * 64 * 50000 / el, "unit": "chain-steps/s", "wall_s": el, "timing": "host wall clock around mcmc.run",
+           "first_U": float(pe[:, 0].mean()), "last_U": float(pe[:, -1].mean()), "U_at_mode": -3283.0,
+           "converged": False, "gpu_launches": 4,
+           "note": "unconverged by construction: U(-2,2) start with identity factor; the reference's own runs use 10^6 warm-up steps"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        q0 = c_oracle.init_uniform(1, 64, 26, dt=np.float32)
+        st = onp.arwmh_init(onp.make_potential("diamonds", **data), q0)
+        Tc = 1000
+        t0 = time.perf_counter()
+        c_oracle.arwmh_run(st, "diamonds", Tc, seed=1, n_threads=cores, collect=False, **data)
+        ct = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 64 * Tc / ct, "unit": "chain-steps/s", "cores": cores, "kind": "port",
+                               "sample": f"the same 64 chains x {Tc} of the 50,000 steps, C oracle (OpenMP over chains), {ct:.1f} s"}
+    return res
+
+
+def run_pooled_check(args, world, rank, dev, K, W):
+    """Correctness of the NCCL pooled-adaptation path on hardware: a FIXED GLOBAL problem (8,192 diamonds chains, Philox
+    streams keyed by the global chain id, 6 pooled windows of 50 steps) sharded over the ranks must give the same shared
+    adaptation state as the same global chains on one GPU.  With one rank this prints the single-GPU result; the values
+    are comparable across the N = 1, 2, 4, 8 lines of a scaling run (sums are float64, so only the summation order differs)."""
+    import numpy as np
+    import torch
+
+    import adaptive_mcmc_b200 as am
+    from adaptive_mcmc_b200.parallel import PooledARWMH, shard_chains
+
+    total = 8192
+    data = am.models.synthetic_diamonds(n=5000, k=25, seed=0)
+    X, Y = data["X"], data["Y"]
+    Xc = np.column_stack([np.ones(len(Y)), X[:, 1:] - X[:, 1:].mean(0)])
+    mode = np.concatenate([np.linalg.lstsq(Xc, Y, rcond=None)[0], [np.log(0.123)]])
+    q_all = mode[None] + 0.01 * np.random.default_rng(123).normal(size=(total, 26))
+    cnt, off = shard_chains(total, rank, world)
+    s = PooledARWMH(am.models.diamonds, num_chains=cnt, pool_every=50, device=dev, chain_offset=off,
+                    init_strategy=am.init_to_value(torch.from_numpy(q_all[off:off + cnt])))
+    s.init(7, model_kwargs=data)
+    s.scale.mul_(0.01)
+    s.cov.mul_(1e-4)
+    for _ in range(6):
+        s.run_window(50, collect=())
+    zsum = s.batch.z.double().abs().sum().reshape(1)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(zsum)
+    return {"workload": "pooled adaptation, 8,192 GLOBAL diamonds chains sharded over the ranks, 6 windows x 50 steps (tcgen05 kernel + "
+                        "statistics + all-reduce + update)", "global_chains": total, "log_step_size": round(float(s.log_step_size), 6),
+            "loc0": round(float(s.loc[0]), 6), "trace_cov": float(f"{float(torch.trace(s.cov)):.6e}"),
+            "sum_abs_z": float(f"{float(zsum):.8e}"), "mean_accept": round(float(s.stats[-1] / s.stats[0]), 5),
+            "expect": "identical across N up to the float64 summation order of the pooled statistics"}
+
+
+def _issue_roofline(key, rate_per_gpu, clk, dev):
+    import torch
+
+    ip = os.path.join(ROOT, "profiles", "instr.json")
+    ent = json.load(open(ip)).get(key) if os.path.exists(ip) else None
+    if not ent:
+        return None
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or 1965.0
+    peak = 4 * sms * mhz * 1e6  # warp-instructions per second, one per scheduler per cycle
+    achieved = rate_per_gpu * ent["thread_inst_per_chain_step"] / 32.0
+    return {"bound": "issue", "achieved": achieved, "peak": peak, "unit": "warp-inst/s", "frac": achieved / peak,
+            "thread_inst_per_chain_step": ent["thread_inst_per_chain_step"], "source": ent["source"],
+            "note": "peak = 4 schedulers x SMs x sampled SM clock; instruction count from the ncu capture named in `source`"}
 
 
 def _traffic(key):

@@ -9,6 +9,7 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference/python"
 
 
@@ -36,6 +37,9 @@ def load_jax_pickle(path):
 
 def main():
     out = {}
+    prev = os.path.join(HERE, "reference_pins.json")
+    if os.path.exists(prev):  # keys transcribed by hand from the notebooks (quality_tables) are kept as they are
+        out = json.load(open(prev))
     # (1) eight_schools ARWMH posterior table, python/jupyter/posteriordb_eight-schools.ipynb:L855-865
     out["eight_schools_arwmh_table"] = {
         "source": "python/jupyter/posteriordb_eight-schools.ipynb:L855-865 (50k warmup + 500k samples, thin 50)",
@@ -68,6 +72,24 @@ def main():
             "mean": x.mean(0).tolist(),
             "std": x.std(0, ddof=1).tolist(),
             "cov_cond": float(np.linalg.cond(np.cov(x.T))),
+            # NOT used by the recovery below -- an independent check of the restated model (sigma couples to the weakly
+            # identified coefficients only through the N(0,1) prior of b)
+            "corr_logsigma_beta": np.corrcoef(np.column_stack([x[:, 25], x[:, :25]]).T)[0, 1:].tolist(),
+        }
+        # (5) a diamonds-equivalent data set: the Gaussian-linear likelihood depends on the data only through
+        #     (N, Xc^T Xc, Xc^T Y, sum Y, Y^T Y); recover them from the draws' mean / covariance / E[sigma^2]
+        #     (oracle/diamonds_exact.py) -- posteriordb's diamonds.json itself is not in the image.
+        if ROOT not in sys.path:
+            sys.path.insert(0, ROOT)
+        from oracle import diamonds_exact as de
+
+        st = de.recover_stats_from_draws(x, n=5000)
+        pm = de.posterior_moments(st)
+        out["diamonds_recovered_stats"] = {
+            "source": "recovered from diamonds-example-references.pkl by oracle/diamonds_exact.py:recover_stats_from_draws "
+                      "(N = 5000 from posteriordb_diamonds.ipynb:L1452); X1 = [1 | Xc], G = X1^T X1, h = X1^T Y",
+            "n": 5000, "G": st["G"].tolist(), "h": st["h"].tolist(), "yy": st["yy"],
+            "exact_mean": pm["mean"].tolist(), "exact_std": np.sqrt(np.diag(pm["cov"])).tolist(),
         }
     with open(os.path.join(HERE, "reference_pins.json"), "w") as f:
         json.dump(out, f, indent=1)

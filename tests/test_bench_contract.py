@@ -22,3 +22,6 @@ def test_reference_arm_prints_one_json_line(built):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"]
+    # same chain count as the GPU arm, its own min-ESS/s, and the probe for the real (JAX) reference is reported
+    assert line["config"]["chains_per_gpu"] == 65536 and line["min_ess_per_sec"] > 0
+    assert line["jax_probe"]["available"] in (True, False) and "detail" in line["jax_probe"]
