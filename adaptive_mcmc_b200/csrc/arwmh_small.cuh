@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "models.cuh"
 
+
 namespace amcmc {
 
 template <typename R, int D> struct ChainRegs {
@@ -34,8 +35,13 @@ AMCMC_HD constexpr int tri_full(int i, int j) { return i * (i + 1) / 2 + j; }   
 //   g = D_j + c w_j^2 t;  D_j' = g;  coef = c w_j t / g;  t <- D_j t / g;
 //   w_i -= w_j Lt_ij;  Lt_ij += coef w_i   (i > j)
 // WANT additionally accumulates |L' e^lam' - L e^lam|_F^2 (arwmh.py:197) on the fly.
+//
+// `bump` (0 or 1) is added to the pivot before its reciprocal.  The hot loop runs the sweep UNCONDITIONALLY: when the
+// reference would keep the old factor (arwmh.py:191) the caller passes gamma = 0, w = 0, bump = 1, and every expression
+// below then reproduces the old factor bit for bit (Dj = D, g = D, coef = 0 * finite = 0, Ln = Lo) -- no branch, no
+// second register copy of the factor.  The bump only keeps 0 * rcp(0) = NaN out when a pivot is exactly zero.
 template <typename R, int D, bool WANT>
-AMCMC_HD R rank1_sweep(ChainRegs<R, D>& s, R (&w)[D], R gamma, R el_old, R el_new) {
+AMCMC_HD R rank1_sweep(ChainRegs<R, D>& s, R (&w)[D], R gamma, R el_old, R el_new, R bump = (R)0) {
   R t = (R)1;
   const R omg = (R)1 - gamma;
   R ss = (R)0;
@@ -46,7 +52,7 @@ AMCMC_HD R rank1_sweep(ChainRegs<R, D>& s, R (&w)[D], R gamma, R el_old, R el_ne
     const R wj = w[j];
     const R cw = gamma * wj;
     const R g = fma(cw * wj, t, Dj);
-    const R tr = t * Num<R>::rcp(g);
+    const R tr = t * Num<R>::rcp(g + bump);
     const R coef = cw * tr;
     t = Dj * tr;
     s.Dg[j] = g;
@@ -86,9 +92,11 @@ template <typename R, int D> AMCMC_HD R factor_frob2(const ChainRegs<R, D>& s) {
 }
 
 // One ARWMH.sample (python/kernels/arwmh.py:140-207) for the chain held in `s`.
-template <class Model, typename R, bool ADAPT>
+// WANT_ASC: also compute as_change (:197) -- only the last step of a launch does (state snapshots are launch boundaries),
+// so the hot loop instantiates WANT_ASC = false, which is straight-line code.
+template <class Model, typename R, bool ADAPT, bool WANT_ASC>
 AMCMC_HD bool arwmh_step(ChainRegs<R, Model::D>& s, const Model& m, const R (&z)[Model::D], R u, R nf,
-                         bool n_is_one, R lr_decay, R target, R eps, bool want_asc) {
+                         bool n_is_one, R lr_decay, R target, R eps) {
   constexpr int D = Model::D;
   const R el = Num<R>::exp(s.lam);
   // :166-167  x' = x + (L e^lam + eps I) z,  L z = Lt (sqrt(Dg) .* z)
@@ -135,7 +143,7 @@ AMCMC_HD bool arwmh_step(ChainRegs<R, Model::D>& s, const Model& m, const R (&z)
   const R lam_new = fma(gamma, alpha - target, s.lam);
   // :190-191 rank-one update; "NaN => keep the old factor" is applied as a pre-condition
   // (gamma == 1 <=> zero scaled diagonal, non-positive pivot, non-finite delta), see DESIGN.md.
-  if (want_asc) {
+  if (WANT_ASC) {
     const R el_new = Num<R>::exp(lam_new);
     R ss;
     if (ok) {
@@ -145,8 +153,11 @@ AMCMC_HD bool arwmh_step(ChainRegs<R, Model::D>& s, const Model& m, const R (&z)
       ss = de * de * factor_frob2(s);
     }
     s.asc = Num<R>::sqrt(ss);  // :197
-  } else if (ok) {
-    rank1_sweep<R, D, false>(s, w, gamma, el, el);
+  } else {
+    // branch-free: a kept factor is the sweep with gamma = 0, w = 0 (see rank1_sweep)
+#pragma unroll
+    for (int k = 0; k < D; ++k) w[k] = ok ? w[k] : (R)0;
+    rank1_sweep<R, D, false>(s, w, ok ? gamma : (R)0, el, el, ok ? (R)0 : (R)1);
   }
   s.lam = lam_new;
   return acc;
@@ -221,53 +232,105 @@ AMCMC_HD void store_chain(const ChainRegs<R, D>& s, const StateView<R>& st, int6
   st.asc[c] = s.asc;
 }
 
-// The whole per-chain launch body (host-compilable for tests/hostsim).
-template <class Model, typename R, bool ADAPT, bool EXTERNAL>
+// Draws of one step: external arrays (shared-draw parity mode) or the Philox stream.
+template <typename R, int D, bool EXTERNAL>
+AMCMC_HD void step_draws(const RunView<R>& a, const Philox& rng, int64_t C, int64_t c, int64_t t, R (&z)[D], R& u) {
+  if (EXTERNAL) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) z[k] = a.normals[(t * D + k) * C + c];
+    u = a.uniforms[t * C + c];
+  } else {
+    philox_draws<R, D>(rng, (uint64_t)(a.i0 + t), z, u);
+  }
+}
+
+// Steps [t0, t1) of the launch without any collection logic: the hot loop.  n follows arwmh.py:180-181 (it restarts at
+// 1 after the warm-up); the frozen kernel (sample_Pnx, pooled windows) averages its acceptance rate over THIS launch.
+template <class Model, typename R, bool ADAPT, bool EXTERNAL, bool PIPE>
+AMCMC_HD void arwmh_steps(ChainRegs<R, Model::D>& s, const Model& m, const RunView<R>& a, const Philox& rng, int64_t C,
+                          int64_t c, int64_t t0, int64_t t1) {
+  constexpr int D = Model::D;
+  // Software pipelining of the counter RNG: the draws of step t + 1 do not depend on the chain, so they are generated
+  // next to the (serially dependent) rank-one sweep of step t -- independent work for the instruction scheduler.
+  if (PIPE && !EXTERNAL) {
+    if (t0 >= t1) return;
+    R z[D], u;
+    step_draws<R, D, false>(a, rng, C, c, t0, z, u);
+    for (int64_t t = t0; t < t1; ++t) {
+      const int64_t i = a.i0 + t;
+      R zn[D], un;
+      step_draws<R, D, false>(a, rng, C, c, t + 1, zn, un);  // (one unused set at the end of a segment)
+      const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
+      const R nf = ADAPT ? (R)n : (R)(t + 1);
+      const bool acc = arwmh_step<Model, R, ADAPT, false>(s, m, z, u, nf, n == 1, a.lr_decay, a.target, a.eps);
+      if (a.out_acc) a.out_acc[t * C + c] = (uint8_t)acc;
+#pragma unroll
+      for (int k = 0; k < D; ++k) z[k] = zn[k];
+      u = un;
+    }
+    return;
+  }
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t i = a.i0 + t;
+    R z[D], u;
+    step_draws<R, D, EXTERNAL>(a, rng, C, c, t, z, u);
+    const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
+    const R nf = ADAPT ? (R)n : (R)(t + 1);
+    const bool acc = arwmh_step<Model, R, ADAPT, false>(s, m, z, u, nf, n == 1, a.lr_decay, a.target, a.eps);
+    if (a.out_acc) a.out_acc[t * C + c] = (uint8_t)acc;
+  }
+}
+
+// The whole per-chain launch body (host-compilable for tests/hostsim).  The launch is cut at the collection points
+// (numpyro.util.fori_collect as used at python/utils/kernel_utils.py:29-32: sample k = state after
+// collect_start + (k+1) thinning steps) so that the hot loop carries no collection bookkeeping, and its last step is
+// peeled: it alone computes as_change (arwmh.py:197).
+template <class Model, typename R, bool ADAPT, bool EXTERNAL, bool PIPE = false>
 AMCMC_HD void arwmh_chain_run(const Model& m, const StateView<R>& st, const RunView<R>& a, int64_t c) {
   constexpr int D = Model::D;
   const int64_t C = st.C;
   ChainRegs<R, D> s;
   load_chain(s, st, c);
   const Philox rng(a.seed, (uint64_t)(c + a.chain_offset));
-  int64_t until_collect = a.collect_start + a.thinning;
+  const int64_t T = a.n_steps;
+  int64_t next_collect = a.collect_start + a.thinning;  // number of completed steps at which the next sample is taken
   int64_t sidx = 0;
-  for (int64_t t = 0; t < a.n_steps; ++t) {
-    const int64_t i = a.i0 + t;
-    R z[D], u;
-    if (EXTERNAL) {
-#pragma unroll
-      for (int k = 0; k < D; ++k) z[k] = a.normals[(t * D + k) * C + c];
-      u = a.uniforms[t * C + c];
-    } else {
-      philox_draws<R, D>(rng, (uint64_t)i, z, u);
+  int64_t t = 0;
+  while (t < T) {
+    const int64_t seg_end = next_collect < T ? next_collect : T;
+    const int64_t hot_end = seg_end < T ? seg_end : T - 1;
+    arwmh_steps<Model, R, ADAPT, EXTERNAL, PIPE>(s, m, a, rng, C, c, t, hot_end);
+    t = hot_end;
+    if (seg_end == T) {  // the last step of the launch
+      const int64_t i = a.i0 + t;
+      R z[D], u;
+      step_draws<R, D, EXTERNAL>(a, rng, C, c, t, z, u);
+      const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
+      const R nf = ADAPT ? (R)n : (R)(t + 1);
+      const bool acc = arwmh_step<Model, R, ADAPT, true>(s, m, z, u, nf, n == 1, a.lr_decay, a.target, a.eps);
+      if (a.out_acc) a.out_acc[t * C + c] = (uint8_t)acc;
+      t = T;
     }
-    // :180-181  n restarts at 1 after warmup
-    const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
-    const bool last = (t == a.n_steps - 1);
-    // frozen kernel (sample_Pnx, pooled windows): mean_accept_prob is the mean over THIS launch (the reference discards it)
-    const R nf = ADAPT ? (R)n : (R)(t + 1);
-    const bool acc = arwmh_step<Model, R, ADAPT>(s, m, z, u, nf, n == 1, a.lr_decay, a.target, a.eps, last);
-    if (a.out_acc) a.out_acc[t * C + c] = (uint8_t)acc;
-    if (--until_collect == 0) {
-      until_collect = a.thinning;
+    if (t == next_collect) {
       if (a.out_z) {
 #pragma unroll
         for (int k = 0; k < D; ++k) a.out_z[(sidx * D + k) * C + c] = s.x[k];
       }
       if (a.out_pe) a.out_pe[sidx * C + c] = s.U;
       ++sidx;
+      next_collect += a.thinning;
     }
   }
   store_chain<R, D, ADAPT>(s, st, c);
 }
 
 #ifdef __CUDACC__
-template <class Model, typename R, bool ADAPT, bool EXTERNAL>
+template <class Model, typename R, bool ADAPT, bool EXTERNAL, bool PIPE = false>
 __global__ void __launch_bounds__(64, (sizeof(R) == 4 ? 7 : 1))
 arwmh_small_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st.C) return;
-  arwmh_chain_run<Model, R, ADAPT, EXTERNAL>(m, st, a, c);
+  arwmh_chain_run<Model, R, ADAPT, EXTERNAL, PIPE>(m, st, a, c);
 }
 
 // ARWMH.init (python/kernels/arwmh.py:111-136): q0 ~ U(-r, r)^d (unless given), U0, loc = q0, scale = I, ...

@@ -48,7 +48,17 @@ def test_run_host_asss_external_draws(T):
     nrm = torch.randn(T, Cn, d + 1, generator=g)
     uni = torch.rand(T, Cn, 52, generator=g)
     dn, du = s._draws_to_device_layout((nrm, uni))  # [T][d+1][C], [T][52][C]
-    raw = s.run_batch(b, T, thinning=5, draws=(dn, du))
+    # the host entry cuts the run into chunks of ceil(2048 / thinning) samples; a launch boundary converts the carried
+    # LDL^T factor to the ABI's Cholesky form and back (a rounding), so the device-pointer run is cut at the same steps
+    zs, pes, t0 = [], [], 0
+    while t0 < T:
+        n = min(410 * 5, T - t0)
+        if T - t0 - n < 5:  # the last chunk also takes the uncollected tail
+            n = T - t0
+        raw = s.run_batch(b, n, thinning=5, draws=(dn[t0:t0 + n].contiguous(), du[t0:t0 + n].contiguous()))
+        zs.append(raw["z"]); pes.append(raw["potential_energy"])
+        t0 += n
+    raw = dict(z=torch.cat(zs), potential_energy=torch.cat(pes))
     hn, hu = dn.cpu().contiguous().pin_memory(), du.cpu().contiguous().pin_memory()
     hs = _host_state(b, host)
     hs.i = 0
