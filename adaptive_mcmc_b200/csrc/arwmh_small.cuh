@@ -244,32 +244,13 @@ AMCMC_HD void step_draws(const RunView<R>& a, const Philox& rng, int64_t C, int6
   }
 }
 
-// Steps [t0, t1) of the launch without any collection logic: the hot loop.  n follows arwmh.py:180-181 (it restarts at
+// Steps [t0, t1) of the launch without any collection logic: the hot loop.  (Generating the draws of step t + 1 next to
+// the sweep of step t -- software pipelining of the counter RNG -- was measured: 3.33e10 vs 3.36e10 chain-steps/s, not kept.)  n follows arwmh.py:180-181 (it restarts at
 // 1 after the warm-up); the frozen kernel (sample_Pnx, pooled windows) averages its acceptance rate over THIS launch.
-template <class Model, typename R, bool ADAPT, bool EXTERNAL, bool PIPE>
+template <class Model, typename R, bool ADAPT, bool EXTERNAL>
 AMCMC_HD void arwmh_steps(ChainRegs<R, Model::D>& s, const Model& m, const RunView<R>& a, const Philox& rng, int64_t C,
                           int64_t c, int64_t t0, int64_t t1) {
   constexpr int D = Model::D;
-  // Software pipelining of the counter RNG: the draws of step t + 1 do not depend on the chain, so they are generated
-  // next to the (serially dependent) rank-one sweep of step t -- independent work for the instruction scheduler.
-  if (PIPE && !EXTERNAL) {
-    if (t0 >= t1) return;
-    R z[D], u;
-    step_draws<R, D, false>(a, rng, C, c, t0, z, u);
-    for (int64_t t = t0; t < t1; ++t) {
-      const int64_t i = a.i0 + t;
-      R zn[D], un;
-      step_draws<R, D, false>(a, rng, C, c, t + 1, zn, un);  // (one unused set at the end of a segment)
-      const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
-      const R nf = ADAPT ? (R)n : (R)(t + 1);
-      const bool acc = arwmh_step<Model, R, ADAPT, false>(s, m, z, u, nf, n == 1, a.lr_decay, a.target, a.eps);
-      if (a.out_acc) a.out_acc[t * C + c] = (uint8_t)acc;
-#pragma unroll
-      for (int k = 0; k < D; ++k) z[k] = zn[k];
-      u = un;
-    }
-    return;
-  }
   for (int64_t t = t0; t < t1; ++t) {
     const int64_t i = a.i0 + t;
     R z[D], u;
@@ -285,7 +266,7 @@ AMCMC_HD void arwmh_steps(ChainRegs<R, Model::D>& s, const Model& m, const RunVi
 // (numpyro.util.fori_collect as used at python/utils/kernel_utils.py:29-32: sample k = state after
 // collect_start + (k+1) thinning steps) so that the hot loop carries no collection bookkeeping, and its last step is
 // peeled: it alone computes as_change (arwmh.py:197).
-template <class Model, typename R, bool ADAPT, bool EXTERNAL, bool PIPE = false>
+template <class Model, typename R, bool ADAPT, bool EXTERNAL>
 AMCMC_HD void arwmh_chain_run(const Model& m, const StateView<R>& st, const RunView<R>& a, int64_t c) {
   constexpr int D = Model::D;
   const int64_t C = st.C;
@@ -299,7 +280,7 @@ AMCMC_HD void arwmh_chain_run(const Model& m, const StateView<R>& st, const RunV
   while (t < T) {
     const int64_t seg_end = next_collect < T ? next_collect : T;
     const int64_t hot_end = seg_end < T ? seg_end : T - 1;
-    arwmh_steps<Model, R, ADAPT, EXTERNAL, PIPE>(s, m, a, rng, C, c, t, hot_end);
+    arwmh_steps<Model, R, ADAPT, EXTERNAL>(s, m, a, rng, C, c, t, hot_end);
     t = hot_end;
     if (seg_end == T) {  // the last step of the launch
       const int64_t i = a.i0 + t;
@@ -325,12 +306,12 @@ AMCMC_HD void arwmh_chain_run(const Model& m, const StateView<R>& st, const RunV
 }
 
 #ifdef __CUDACC__
-template <class Model, typename R, bool ADAPT, bool EXTERNAL, bool PIPE = false>
+template <class Model, typename R, bool ADAPT, bool EXTERNAL>
 __global__ void __launch_bounds__(64, (sizeof(R) == 4 ? 7 : 1))
 arwmh_small_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st.C) return;
-  arwmh_chain_run<Model, R, ADAPT, EXTERNAL, PIPE>(m, st, a, c);
+  arwmh_chain_run<Model, R, ADAPT, EXTERNAL>(m, st, a, c);
 }
 
 // ARWMH.init (python/kernels/arwmh.py:111-136): q0 ~ U(-r, r)^d (unless given), U0, loc = q0, scale = I, ...

@@ -1,6 +1,5 @@
 // launch_small.cuh -- host-side launch helpers for the thread-per-chain kernels.
 #pragma once
-#include <cstdlib>
 #include "arwmh_small.cuh"
 #include "asss_small.cuh"
 #include "internal.h"
@@ -60,9 +59,7 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
     return check_cuda(cudaGetLastError(), "asss_small_kernel launch");
   }
   if (a->adapt) {
-    static const bool pipe = [] { const char* e = getenv("AMCMC_SMALL_PIPE"); return e && atoi(e) != 0; }();  // A/B switch
     if (ext) arwmh_small_kernel<Model, R, true, true><<<grid, block, 0, s>>>(m, sv, rv);
-    else if (pipe) arwmh_small_kernel<Model, R, true, false, true><<<grid, block, 0, s>>>(m, sv, rv);
     else     arwmh_small_kernel<Model, R, true, false><<<grid, block, 0, s>>>(m, sv, rv);
   } else {
     if (ext) arwmh_small_kernel<Model, R, false, true><<<grid, block, 0, s>>>(m, sv, rv);

