@@ -37,6 +37,8 @@ struct TcAdaptParams {
   int64_t num_warmup;
   float lr_decay, target, eps;
   int rnd_begin, rnd_end;  // rounds (sets of TC_GR groups per CTA) served by this launch
+  uint32_t x_bytes;        // bytes fetched per design-matrix tile (TCA_TILE_BYTES; less only in the traffic experiment)
+  uint32_t dbg;            // timing experiments (results wrong): 2 = two MMAs per accumulator, 4 = no factor pass
 };
 
 __device__ __forceinline__ int tri_f(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -206,13 +208,23 @@ constexpr int TCA_K = 64;
 constexpr int TCA_TILE_BYTES = TC_TILE_N * TCA_K * 2;  // 32768
 constexpr int TCA_A_BYTES = TC_M * TCA_K * 2;          // 16384
 constexpr int TCA_STAGES = 2;                          // design-matrix tiles in flight (a third stage was measured: no gain)
+// Accumulators: 128 data rows (UMMA N = 128) each, FOUR in flight in the 512 TMEM columns.  With two 256-column
+// accumulators the MMA thread, the tensor pipe and the drain formed one serial chain per accumulator (measured with the
+// phase clocks: 1,440 cycles per 256-row tile and group against 768 cycles of tensor work -- MMA issue, then a wait for
+// the drain of the accumulator before last); four half-size accumulators give that chain two more slots of slack.
+#ifndef AMCMC_TCA_ACC_N
+#define AMCMC_TCA_ACC_N 128
+#endif
+constexpr int TCA_ACC_N = AMCMC_TCA_ACC_N;             // 128 (four accumulators in flight) or 256 (two)
+constexpr int TCA_NBUF = 512 / TCA_ACC_N;
+constexpr int TCA_HALVES = TC_TILE_N / TCA_ACC_N;      // accumulators per design-matrix tile and group
 struct TcaSmem {
   static constexpr int OFF_X = 0;                                // TCA_STAGES stages
   static constexpr int OFF_A = TCA_STAGES * TCA_TILE_BYTES;      // TC_GR groups
   static constexpr int OFF_BAR = OFF_A + TC_GR * TCA_A_BYTES;    // x_full[2], x_empty[2], (4 unused), a_ready, v_full, v_empty
   static constexpr int OFF_TMEM = OFF_BAR + TcSmem::N_BAR * 8;
-  static constexpr int OFF_ACCBAR = OFF_TMEM + 16;               // acc_full[4], acc_empty[4]
-  static constexpr int OFF_V = OFF_ACCBAR + 64;                  // float [TC_GR][27][TC_M]
+  static constexpr int OFF_ACCBAR = OFF_TMEM + 16;               // acc_full[2][TCA_NBUF], acc_empty[2][TCA_NBUF]
+  static constexpr int OFF_V = OFF_ACCBAR + 2 * 2 * TCA_NBUF * 8;  // float [TC_GR][27][TC_M]
   static constexpr int BYTES = OFF_V + TC_GR * 27 * TC_M * 4;
 };
 
@@ -271,10 +283,13 @@ static_assert(TC_EPI_WARPS == 8 && TC_HELP_WARPS == 2, "warp roles assume 8 samp
 static_assert(32 * TC_EPI_WARPS * kSamplerRegs + 128 * kServiceRegs <= TC_THREADS * kLaunchRegs, "the pool is what the CTA got at launch");
 
 #ifdef AMCMC_TC_TIMING
-__device__ unsigned long long tc_dbg[16];
-#define TC_T(k) do { if (dbg) { const long long now_ = clock64(); tc_dbg[k] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
+__device__ unsigned long long tc_dbg[64];
+// phase clocks go to shared memory (a global read-modify-write per sample would itself cost ~1000 cycles) and are flushed once
+#define TC_T(k) do { if (dbg) { const long long now_ = clock64(); s_dbg[k] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
+#define TC_W(k) do { if (dbg) { const long long now_ = clock64(); s_dbg_w[k] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
 #else
 #define TC_T(k) do { } while (0)
+#define TC_W(k) do { } while (0)
 #endif
 
 template <bool EXTERNAL>
@@ -286,10 +301,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TcaSmem::OFF_BAR);
   uint64_t* x_full = bars;          // [TCA_STAGES] (the slots of the unused acc barriers of the shared layout follow)
   uint64_t* x_empty = bars + 4;     // [TCA_STAGES]
-  // accumulator hand-off, per stream and TMEM buffer: [stream * 2 + buffer].  Both streams use both buffers; a
+  // accumulator hand-off, per stream and TMEM buffer: [stream * TCA_NBUF + buffer].  Both streams use all buffers; a
   // waiter on an mbarrier parity may lag at most one phase, so the streams cannot share one barrier ring.
   uint64_t* acc_full = reinterpret_cast<uint64_t*>(smem + TcaSmem::OFF_ACCBAR);
-  uint64_t* acc_empty = acc_full + 4;
+  uint64_t* acc_empty = acc_full + 2 * TCA_NBUF;
   uint64_t* a_ready = bars + 8;
   uint64_t* v_full = bars + 8 + TC_GR;
   uint64_t* v_empty = bars + 8 + 2 * TC_GR;
@@ -298,6 +313,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler the role branches are warp-uniform
+#ifdef AMCMC_TC_TIMING
+  __shared__ unsigned long long s_dbg[64];
+  if (tid < 64) s_dbg[tid] = 0;
+#endif
   // Group ownership is interleaved: CTA b owns groups b, b + grid, b + 2 grid, ...  The first two groups of every CTA
   // are then the first 2 * grid groups of the factor buffer -- the contiguous prefix the host pins in L2 -- and both
   // streams of a CTA (groups 0, 2 / groups 1, 3) get one pinned and one streaming group each.
@@ -308,9 +327,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
       mbar_init(&x_full[s], 1);
       mbar_init(&x_empty[s], 1);
     }
-    for (int s = 0; s < 4; ++s) {
+    for (int s = 0; s < 2 * TCA_NBUF; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 32 * TC_EPI_WARPS / 2);  // the four sampler warps of the owning stream
+      mbar_init(&acc_empty[s], TC_EPI_WARPS / 2);  // one arrival from each of the four sampler warps of the owning stream
     }
     for (int g = 0; g < TC_GR; ++g) {
       mbar_init(&a_ready[g], TC_M);
@@ -351,43 +370,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
           for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
             const int s = x_it % TCA_STAGES;
             mbar_wait(&x_empty[s], ((x_it / TCA_STAGES) & 1) ^ 1);
-            mbar_arrive_expect_tx(&x_full[s], TCA_TILE_BYTES);
-            tma_load_1d(sX + s * TCA_TILE_BYTES, ap.Xcanon64 + (size_t)tile * (TCA_TILE_BYTES / 2), TCA_TILE_BYTES, &x_full[s]);
+            mbar_arrive_expect_tx(&x_full[s], ap.x_bytes);
+            tma_load_1d(sX + s * TCA_TILE_BYTES, ap.Xcanon64 + (size_t)tile * (TCA_TILE_BYTES / 2), ap.x_bytes, &x_full[s]);
           }
       }
       TC_ROUND_END
     } else if (warp == kMmaWarp) {
       TC_ROUND_BEGIN
       if (lane == 0) {  // ===== MMA issuer =====
-        const uint32_t idesc = make_idesc_bf16_f32(TC_M, TC_TILE_N);
+#ifdef AMCMC_TC_TIMING
+        const bool dbg = (blockIdx.x == 0);
+        long long tlast = clock64();
+#endif
+        const uint32_t idesc = make_idesc_bf16_f32(TC_M, TCA_ACC_N);
         constexpr uint32_t a_kstride = (TC_M / 8) * 128, b_kstride = (TC_TILE_N / 8) * 128;
+        // base descriptors (group 0 / stage 0 / rows 0..): the loops below only add chunk offsets to the low words
+        const uint64_t da0 = make_smem_desc(smem_u32(sA), a_kstride, 128), db0 = make_smem_desc(smem_u32(sX), b_kstride, 128);
+        const uint32_t da_lo0 = (uint32_t)da0, da_hi = (uint32_t)(da0 >> 32), db_lo0 = (uint32_t)db0, db_hi = (uint32_t)(db0 >> 32);
+        constexpr uint32_t kAChunk = (2 * a_kstride) >> 4, kBChunk = (2 * b_kstride) >> 4;  // one K = 16 chunk, in descriptor units
         for (int64_t st = 0; st < p.n_steps; ++st)
         for (int strm = 0; strm < 2; ++strm) {  // stream = groups strm, strm + 2 (see the sampler warps)
           if (strm >= G) break;
           for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
             const int s = x_it % TCA_STAGES;
+            TC_T(11);
             mbar_wait(&x_full[s], (x_it / TCA_STAGES) & 1);
+            TC_T(8);
             for (int g = strm; g < G; g += 2) {
               if (tile == 0) mbar_wait(&a_ready[g], (a_it + (uint32_t)st) & 1);
-              uint32_t& k = strm ? ks1 : ks0;
-              const int b = k & 1;
-              // TMEM buffer b must be drained by its previous users: this stream's accumulator k-2 and, right after a
-              // stream switch, the other stream's last one in this buffer.  uses(s, b) = (k_s + 1 - b) >> 1.
-              const uint32_t u_own = (k + 1 - b) >> 1, u_oth = ((strm ? ks0 : ks1) + 1 - b) >> 1;
-              if (u_own) mbar_wait(&acc_empty[strm * 2 + b], (u_own - 1) & 1);
-              if (u_oth) mbar_wait(&acc_empty[(strm ^ 1) * 2 + b], (u_oth - 1) & 1);
-              tc_fence_after();
-              const uint32_t a_base = smem_u32(sA + g * TCA_A_BYTES), b_base = smem_u32(sX + s * TCA_TILE_BYTES);
+              TC_T(9);
+              const uint32_t a_lo = da_lo0 + (uint32_t)g * (TCA_A_BYTES >> 4);
 #pragma unroll
-              for (int ks = 0; ks < 6; ++ks) {
-                const int ia = ks < 4 ? ks : ks - 4;              // A chunks 0 1 | 2 3 | 0 1   (D_hi | D_lo | D_hi)
-                const int ib = ks < 2 ? ks : ks - 2;              // B chunks 0 1 | 0 1 | 2 3   (X_hi | X_hi | X_lo)
-                const uint64_t da = make_smem_desc(a_base + 2 * ia * a_kstride, a_kstride, 128);
-                const uint64_t db = make_smem_desc(b_base + 2 * ib * b_kstride, b_kstride, 128);
-                umma_bf16(tmem_base + (uint32_t)(b * TC_TILE_N), da, db, idesc, ks > 0);
+              for (int h = 0; h < TCA_HALVES; ++h) {  // rows [TCA_ACC_N h, TCA_ACC_N (h + 1)) of the tile -> one accumulator
+                uint32_t& k = strm ? ks1 : ks0;
+                const int b = k & (TCA_NBUF - 1);
+                // TMEM buffer b must be drained by its previous users: this stream's accumulator k - TCA_NBUF and, after
+                // a stream switch, the other stream's last one in this buffer.  uses(s, b) = #{j < k_s : j mod NBUF = b}.
+                const uint32_t u_own = k / TCA_NBUF, u_oth = ((strm ? ks0 : ks1) + (TCA_NBUF - 1) - b) / TCA_NBUF;
+                if (u_own) mbar_wait(&acc_empty[strm * TCA_NBUF + b], (u_own - 1) & 1);
+                if (u_oth) mbar_wait(&acc_empty[(strm ^ 1) * TCA_NBUF + b], (u_oth - 1) & 1);
+                TC_T(10);
+                tc_fence_after();
+                // canonical K-major tile of 256 rows: row group r / 8 is 128 bytes further, so half h starts 16 groups in
+                const uint32_t b_lo = db_lo0 + (uint32_t)s * (TCA_TILE_BYTES >> 4) + (uint32_t)h * (((TCA_ACC_N / 8) * 128) >> 4);
+                const uint32_t d = tmem_base + (uint32_t)(b * TCA_ACC_N);
+                // A chunks 0 1 | 2 3 | 0 1 (D_hi | D_lo | D_hi)  x  B chunks 0 1 | 0 1 | 2 3 (X_hi | X_hi | X_lo)
+                umma_bf16_lean<false>(d, a_lo, da_hi, b_lo, db_hi, idesc);
+                umma_bf16_lean<true>(d, a_lo + kAChunk, da_hi, b_lo + kBChunk, db_hi, idesc);
+                if (!(ap.dbg & 2u)) {
+                  umma_bf16_lean<true>(d, a_lo + 2 * kAChunk, da_hi, b_lo, db_hi, idesc);
+                  umma_bf16_lean<true>(d, a_lo + 3 * kAChunk, da_hi, b_lo + kBChunk, db_hi, idesc);
+                  umma_bf16_lean<true>(d, a_lo, da_hi, b_lo + 2 * kBChunk, db_hi, idesc);
+                  umma_bf16_lean<true>(d, a_lo + kAChunk, da_hi, b_lo + 3 * kBChunk, db_hi, idesc);
+                }
+                umma_commit(&acc_full[strm * TCA_NBUF + b]);
+                ++k;
               }
-              umma_commit(&acc_full[strm * 2 + b]);
-              ++k;
             }
             umma_commit(&x_empty[s]);
           }
@@ -454,12 +492,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
       }
 
 #ifdef AMCMC_TC_TIMING
-      const bool dbg = (blockIdx.x == 0 && tid == 0);
+      const bool dbg = (blockIdx.x == 0 && lane == 0);
       long long tlast = clock64();
+      unsigned long long* s_dbg_w = s_dbg + 16 + warp * 4;  // per sampler warp: GEMM phase, accept, v_full + pass, proposal
 #endif
       // st = -1 builds the proposal of the first step (no accept, no update)
       for (int64_t st = -1; st < p.n_steps; ++st) {
-        TC_T(0);
+        TC_W(3);
         const int64_t it = p.i0 + st;
         float mine0 = 0.f, mine1 = 0.f;
         if (st >= 0) {
@@ -468,22 +507,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
 #pragma unroll
             for (int l = 0; l < 2; ++l) {
               if (l < n_mine) {
-                const int b = acc_it & 1;
-                mbar_wait(&acc_full[half * 2 + b], (acc_it >> 1) & 1);
-                tc_fence_after();
-                const uint32_t ta = tmem_base + t_lane + (uint32_t)(b * TC_TILE_N);
                 float ss = 0.f;
 #pragma unroll 1
-                for (uint32_t ch = 0; ch < 256u; ch += 128u) ss += epilogue_sumsq_half(ta + ch);  // rolled: 128 live values at a time
-                tc_fence_before();
-                mbar_arrive(&acc_empty[half * 2 + b]);
+                for (int h = 0; h < TCA_HALVES; ++h) {  // rolled: 128 live accumulator values at a time
+                  const int b = acc_it & (TCA_NBUF - 1);
+#ifdef AMCMC_TC_TIMING
+                  const long long td0 = clock64();
+#endif
+                  mbar_wait(&acc_full[half * TCA_NBUF + b], (acc_it / TCA_NBUF) & 1);
+#ifdef AMCMC_TC_TIMING
+                  const long long td1 = clock64();
+#endif
+                  tc_fence_after();
+#pragma unroll 1
+                  for (uint32_t ch = 0; ch < (uint32_t)TCA_ACC_N; ch += 128u)
+                    ss += epilogue_sumsq_half(tmem_base + t_lane + (uint32_t)(b * TCA_ACC_N) + ch);
+                  tc_fence_before();
+                  // one arrival per warp: 128 per-thread arrivals on one mbarrier are 128 serialised shared-memory
+                  // atomics per accumulator
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&acc_empty[half * TCA_NBUF + b]);
+#ifdef AMCMC_TC_TIMING
+                  if (dbg) { s_dbg[48 + warp * 2] += (unsigned long long)(td1 - td0); s_dbg[49 + warp * 2] += (unsigned long long)(clock64() - td1); }
+#endif
+                  ++acc_it;
+                }
                 if (l) mine1 += ss; else mine0 += ss;
-                ++acc_it;
               }
             }
           }
-          TC_T(1);
-          TC_T(2);
+          TC_W(0);
+          
         }
         bool collect_now = false;
         if (st >= 0) {
@@ -558,15 +612,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
             }
             const float* zn = sV + (size_t)g * 27 * TC_M + row;
             float* fcol = ap.ldl + (g0 + g * gs) * (TC_NE * TC_M) + row;
-            TC_T(3);
-            if (last) {
+            TC_W(1);
+            if (ap.dbg & 4u) {
+              if (!last) mbar_wait(&v_full[g], (a_it + (uint32_t)(st + 1)) & 1);
+#pragma unroll
+              for (int k = 0; k < TC_D; ++k) acc[k] = 0.f;
+            }
+            if (ap.dbg & 4u) {
+            } else if (last) {
               const float ss = tc_column_pass<true>(fcol, zn, false, upd, w, gamma, el_old, el_new, acc);
               if (live) ap.asc[c] = sqrtf(ss);  // :197
             } else {
               mbar_wait(&v_full[g], (a_it + (uint32_t)(st + 1)) & 1);
-              TC_T(4);
+              
               tc_column_pass<false>(fcol, zn, true, upd, w, gamma, el_old, el_new, acc);
-              TC_T(5);
+              TC_W(2);
+            }
+            if (!last) {
               // ---- proposal of step st+1 from the current position (arwmh.py:166-167), A' row, energy parts
               const float* xsrc = curA ? p.xprop : p.z;
               float* xdst = curA ? p.z : p.xprop;
@@ -581,7 +643,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
               uaccA = zn[26 * TC_M];
               mbar_arrive(&v_empty[g]);
               tc_emit_proposal(xp, ap.cref + cc, p.C, ap.crss[cc], sA, g, row, &a_ready[g], (double)p.n_rows, p.cst, UppA, i2vA, rssA);
-              TC_T(6);
+              TC_W(3);
             }
           }
           {  // swap the two owned chains
@@ -629,6 +691,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+#ifdef AMCMC_TC_TIMING
+  if (blockIdx.x == 0 && tid < 64) atomicAdd(&tc_dbg[tid], s_dbg[tid]);
+#endif
 }
 
 // from diamonds_tc.cu
@@ -650,6 +715,13 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
   ap.lr_decay = (float)a->lr_decay;
   ap.target = (float)a->target_accept_prob;
   ap.eps = (float)a->eps;
+  ap.x_bytes = TCA_TILE_BYTES;
+  if (const char* e = getenv("AMCMC_TC_EXPERIMENT_X_BYTES")) {  // traffic experiment only (results are then wrong)
+    const long v = atol(e);
+    if (v >= 16 && v <= TCA_TILE_BYTES && v % 16 == 0) ap.x_bytes = (uint32_t)v;
+  }
+  ap.dbg = 0;
+  if (const char* e = getenv("AMCMC_TC_EXPERIMENT_FLAGS")) ap.dbg = (uint32_t)atol(e);
   const int64_t C = st->n_chains;
   if (ex->ldl_groups < ap.p.n_groups) {
     if (ex->ldl) cudaFree(ex->ldl);
@@ -777,7 +849,7 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
 
 #ifdef AMCMC_TC_TIMING
 extern "C" void amcmc_debug_tc_timing(unsigned long long* out, int reset) {
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(amcmc::tc_dbg, z, sizeof(z)); }
-  else cudaMemcpyFromSymbol(out, amcmc::tc_dbg, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(amcmc::tc_dbg, z, sizeof(z)); }
+  else cudaMemcpyFromSymbol(out, amcmc::tc_dbg, sizeof(unsigned long long) * 64);
 }
 #endif

@@ -118,6 +118,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
+// The same with the accumulate flag known at compile time and the descriptors given as (low word, high word): the MMA
+// thread's own instruction stream is what limits a skinny GEMM (few MMAs per accumulator) -- a micro-benchmark
+// (scripts/probes/umma_bench.cu) measures 128 cycles per M = 128, N = 256, K = 16 MMA with hoisted descriptors and 232
+// cycles when every MMA rebuilds its two 64-bit descriptors -- so the hot loops keep one base descriptor per operand
+// and only add the byte offset (>> 4) of the chunk to its low word (the address field is bits 0..13, no carry out).
+template <bool ACCUMULATE>
+__device__ __forceinline__ void umma_bf16_lean(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACCUMULATE ? 1 : 0)
+      : "memory");
+}
+
 // all previously issued MMAs of this thread complete -> one arrival on `bar`
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

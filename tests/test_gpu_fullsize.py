@@ -100,3 +100,71 @@ def test_diamonds_tc_65536_chains_properties():
     U = o.potential_diamonds(zs, X, Y)
     assert np.abs(s1.batch.pe.cpu().numpy()[idx] - U).max() < 1e-2
     assert 0.05 < float(s1.batch.macc.mean()) < 0.8
+
+
+@pytest.mark.parametrize("C", [65536, 131072])
+def test_diamonds_tc_adaptive_full_size_properties(C):
+    """`diamonds_tc_adapt_kernel` (per-chain adaptation = the reference's ARWMH.sample, arwmh.py:140-207) at the chain
+    counts of BASELINE.json configs[2]-style runs (65,536 on one GPU) and of a configs[3] slice (131,072 per GPU):
+    determinism, shard independence under `chain_offset` (the multi-GPU contract), energies against the float64 oracle on a
+    random subset, acceptance band, finite adaptation state.  131,072 chains = 1024 groups = two rounds per CTA."""
+    data = models.synthetic_diamonds(n=5000, k=25, seed=0)
+    X, Y = data["X"], data["Y"]
+    Xc = np.column_stack([np.ones(len(Y)), X[:, 1:] - X[:, 1:].mean(0)])
+    mode = np.concatenate([np.linalg.lstsq(Xc, Y, rcond=None)[0], [np.log(0.123)]])
+    q0 = mode[None] + 0.004 * np.random.default_rng(0).normal(size=(C, 26))
+    T = 300  # more than one 256-step segment: the per-chain GEMM reference points move once
+
+    def run(Cn, offset, q):
+        s = am.ARWMH(models.diamonds, num_chains=Cn, chain_offset=offset, init_strategy=am.init_to_value(torch.from_numpy(q)))
+        s.impl = _lib.IMPL_TENSOR
+        st = s.init(2, num_warmup=0, init_params=None, model_kwargs=data)
+        b = am.ChainBatch.from_state(s.potential, st, copy=False)
+        b.set_dense_scale(torch.eye(26) * 0.002)
+        raw = s.run_batch(b, T, thinning=T, collect=("z", "potential_energy"))
+        return b, raw
+
+    b1, r1 = run(C, 0, q0)
+    b2, r2 = run(C, 0, q0)
+    for f in ("z", "pe", "loc", "scale", "lam", "macc"):
+        assert torch.equal(getattr(b1, f), getattr(b2, f)), f
+    lo = C - 40000  # a shard that straddles group and round boundaries, run alone with its global chain ids
+    b3, r3 = run(384, lo, q0[lo:lo + 384])
+    assert torch.equal(b3.z, b1.z[:, lo:lo + 384]) and torch.equal(b3.scale, b1.scale[:, lo:lo + 384])
+    assert torch.equal(b3.lam, b1.lam[lo:lo + 384]) and torch.equal(r3["potential_energy"], r1["potential_energy"][:, lo:lo + 384])
+    idx = np.random.default_rng(1).choice(C, 384, replace=False)
+    ti = torch.from_numpy(idx).to(b1.z.device)
+    U = o.potential_diamonds(b1.z[:, ti].t().double().cpu().numpy(), X, Y)
+    assert np.abs(b1.pe.cpu().numpy()[idx] - U).max() < 2e-2
+    np.testing.assert_allclose(r1["potential_energy"][-1].cpu().numpy(), b1.pe.cpu().numpy())
+    acc = float(b1.macc.mean())
+    assert 0.1 < acc < 0.5, acc
+    assert torch.isfinite(b1.scale).all() and torch.isfinite(b1.lam).all() and torch.isfinite(b1.loc).all()
+    assert int(b1.i) == T
+
+
+def test_ram_gaussian_16384_chains_properties():
+    """BASELINE.json configs[4] at full size: 16,384 robust-adaptive-Metropolis chains on the d = 200 AR(1) Gaussian."""
+    d, C, T = 200, 16384, 60
+    P = models.ar1_precision_chol(d, 0.9)
+
+    def run(Cn, offset):
+        s = am.RAM(models.gaussian, num_chains=Cn, chain_offset=offset, init_strategy=am.init_to_value(torch.zeros(Cn, d)))
+        st = s.init(4, num_warmup=0, init_params=None, model_kwargs=dict(prec_chol=P))
+        b = am.ChainBatch.from_state(s.potential, st, copy=False)
+        b.scale.mul_(2.38 / d**0.5 * 0.3)
+        raw = s.run_batch(b, T, thinning=T, collect=("z", "potential_energy"))
+        return b, raw
+
+    b1, r1 = run(C, 0)
+    b2, _ = run(C, 0)
+    assert torch.equal(b1.z, b2.z) and torch.equal(b1.scale, b2.scale) and torch.equal(b1.pe, b2.pe)
+    b3, _ = run(96, 9000)
+    assert torch.equal(b3.z, b1.z[:, 9000:9096]) and torch.equal(b3.scale, b1.scale[:, 9000:9096])
+    idx = np.random.default_rng(2).choice(C, 128, replace=False)
+    z = b1.z[:, torch.from_numpy(idx).to(b1.z.device)].t().double().cpu().numpy()
+    U = 0.5 * ((z @ np.tril(np.asarray(P, np.float64))) ** 2).sum(1)
+    np.testing.assert_allclose(b1.pe.cpu().numpy()[idx], U, rtol=2e-4, atol=2e-4)
+    acc = float(b1.macc.mean())
+    assert 0.1 < acc < 0.6, acc
+    assert torch.isfinite(b1.scale).all() and (b1.scale.abs().amax() < 10)

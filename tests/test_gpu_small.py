@@ -141,6 +141,12 @@ def test_kidiq_shared_draws(prec):
     coll, last = sampler.run(state, T, draws=(torch.from_numpy(nrm), torch.from_numpy(uni)), record_accept=True)
     olast, ocoll = co.arwmh_run(ost, "kidiq", T, draws=(nrm, uni), record_accept=True, **data)
     _compare(coll, last, ocoll, olast, tol if prec == "f64" else 5e-3, 1.0 if prec == "f64" else 0.8)
+    if prec == "f32":  # the flips of the fp32 run are exactly the decisions float32 energies (|U| ~ 2e3) cannot resolve
+        import flipcheck
+        pot = o.make_potential("kidiq", **data)
+        o64 = o.arwmh_init(pot, ost.z.astype(np.float64))
+        orc, _ = flipcheck.oracle_steps(o, o64, pot, nrm, uni)
+        flipcheck.analyse(_np(coll["accept"]), _np(coll["potential_energy"]), orc, uni, "kidiq register kernel fp32")
 
 
 def test_potential_entry_point_and_potential_fn_mode():

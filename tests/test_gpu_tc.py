@@ -199,6 +199,10 @@ def test_diamonds_tc_adaptive_matches_oracle(C, diamonds_data):
     same = (acc_g == ocoll["accepts"]).all(axis=0)
     assert same.mean() > 0.93, same.mean()
     assert 0.05 < acc_g.mean() < 0.9
+    # the chains that differ are the ones whose u fell inside the float32 energy error of alpha -- and only those
+    import flipcheck
+    orc, _ = flipcheck.oracle_steps(o, ost, pot, nrm, uni, num_warmup=nw)
+    flipcheck.analyse(acc_g, coll["potential_energy"].cpu().numpy(), orc, uni, f"diamonds tcgen05 adaptive C={C}")
     zg = np.concatenate([v.cpu().numpy().reshape(T, C, -1) for v in coll["z"].values()], axis=-1).astype(np.float64)
     # fp32 state vs the fp64 oracle: the north star's fp32 bar (1e-3 relative), in practice ~1e-5
     assert (np.abs(zg[:, same] - ocoll["z"][:, same]) / (1 + np.abs(ocoll["z"][:, same]))).max() < 1e-3
