@@ -208,12 +208,11 @@ constexpr int TCA_K = 64;
 constexpr int TCA_TILE_BYTES = TC_TILE_N * TCA_K * 2;  // 32768
 constexpr int TCA_A_BYTES = TC_M * TCA_K * 2;          // 16384
 constexpr int TCA_STAGES = 2;                          // design-matrix tiles in flight (a third stage was measured: no gain)
-// Accumulators: 128 data rows (UMMA N = 128) each, FOUR in flight in the 512 TMEM columns.  With two 256-column
-// accumulators the MMA thread, the tensor pipe and the drain formed one serial chain per accumulator (measured with the
-// phase clocks: 1,440 cycles per 256-row tile and group against 768 cycles of tensor work -- MMA issue, then a wait for
-// the drain of the accumulator before last); four half-size accumulators give that chain two more slots of slack.
+// Accumulator width (UMMA N): 256 data rows = one design-matrix tile per accumulator, two accumulators in the 512 TMEM
+// columns, one per MMA issuer.  (-DAMCMC_TCA_ACC_N=128 gives four half-tile accumulators; measured slower, 119 k vs 104 k
+// cycles per step at 65,536 chains: the hand-off cost is per accumulator, not per column.)
 #ifndef AMCMC_TCA_ACC_N
-#define AMCMC_TCA_ACC_N 128
+#define AMCMC_TCA_ACC_N 256
 #endif
 constexpr int TCA_ACC_N = AMCMC_TCA_ACC_N;             // 128 (four accumulators in flight) or 256 (two)
 constexpr int TCA_NBUF = 512 / TCA_ACC_N;
@@ -277,11 +276,22 @@ __device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const 
 // warp 9 = MMA issuer, warps 10-11 = draws.  The sampler warpgroups take the registers the third one gives up
 // (setmaxnreg: 2 x 128 x 208 + 128 x 88 = 384 x 168, the CTA's pool at launch), which is what keeps the unrolled column pass spill-free.
 constexpr int64_t kSegment = 256;  // steps between moves of the GEMM reference point
-constexpr int kTmaWarp = TC_EPI_WARPS, kMmaWarp = TC_EPI_WARPS + 1;
+// Warp roles of the service warpgroup.  TWO MMA issuers: tcgen05.mma issue blocks the issuing thread while the tensor pipe is
+// busy (its queue is one deep: scripts/probes/umma_bench.cu), so with a single issuer every barrier wait, fence and commit
+// between two accumulators idled the tensor pipe -- measured 1,525 cycles per 256-row accumulator for 768 cycles of tensor
+// work.  Issuer A serves the first group of the active stream (TMEM buffers 0 .. NBI-1), issuer B the second
+// (buffers NBI ..): while one waits for its buffer to be drained the other's MMAs run.  The draws come from one warp.
+constexpr int kTmaWarp = TC_EPI_WARPS, kMmaWarp = TC_EPI_WARPS + 1, kDrawWarp = TC_EPI_WARPS + 2, kMmaWarpB = TC_EPI_WARPS + 3;
+constexpr int TCA_NBI = TCA_NBUF / 2;  // TMEM buffers per issuer
 constexpr int kSamplerRegs = 208, kServiceRegs = 88, kLaunchRegs = 168;  // launch: 65536 / 384 rounded down to 8
-static_assert(TC_EPI_WARPS == 8 && TC_HELP_WARPS == 2, "warp roles assume 8 sampler + 4 service warps");
+static_assert(TC_EPI_WARPS == 8 && TC_THREADS == 384, "warp roles assume 8 sampler + 4 service warps");
 static_assert(32 * TC_EPI_WARPS * kSamplerRegs + 128 * kServiceRegs <= TC_THREADS * kLaunchRegs, "the pool is what the CTA got at launch");
 
+#ifdef AMCMC_TC_SPIN
+#define TC_HOT_WAIT mbar_wait_spin
+#else
+#define TC_HOT_WAIT mbar_wait
+#endif
 #ifdef AMCMC_TC_TIMING
 __device__ unsigned long long tc_dbg[64];
 // phase clocks go to shared memory (a global read-modify-write per sample would itself cost ~1000 cycles) and are flushed once
@@ -325,7 +335,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
   if (tid == 0) {
     for (int s = 0; s < TCA_STAGES; ++s) {
       mbar_init(&x_full[s], 1);
-      mbar_init(&x_empty[s], 1);
+      mbar_init(&x_empty[s], 2);  // one commit from each MMA issuer
     }
     for (int s = 0; s < 2 * TCA_NBUF; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
     }
     for (int g = 0; g < TC_GR; ++g) {
       mbar_init(&a_ready[g], TC_M);
-      mbar_init(&v_full[g], 32 * TC_HELP_WARPS);
+      mbar_init(&v_full[g], 32);  // the draw warp
       mbar_init(&v_empty[g], TC_M);
     }
     fence_mbar_init();
@@ -346,7 +356,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
 
   const int n_rounds_all = (g_count + TC_GR - 1) / TC_GR;
   const int n_rounds = n_rounds_all < ap.rnd_end ? n_rounds_all : ap.rnd_end;
-  uint32_t x_it = 0, acc_it = 0, a_it = 0;
+  uint32_t x_it = 0, acc_it = 0, acc_it1 = 0, a_it = 0;  // acc_it / acc_it1: accumulators drained of the stream's first / second group
   uint32_t ks0 = 0, ks1 = 0;  // MMA warp: accumulators issued so far per stream
 
 #define TC_ROUND_BEGIN                                   \
@@ -375,11 +385,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
           }
       }
       TC_ROUND_END
-    } else if (warp == kMmaWarp) {
+    } else if (warp == kMmaWarp || warp == kMmaWarpB) {
+      const int issuer = warp == kMmaWarp ? 0 : 1;
       TC_ROUND_BEGIN
-      if (lane == 0) {  // ===== MMA issuer =====
+      if (lane == 0) {  // ===== MMA issuers =====
 #ifdef AMCMC_TC_TIMING
-        const bool dbg = (blockIdx.x == 0);
+        const bool dbg = (blockIdx.x == 0 && issuer == 0);
         long long tlast = clock64();
 #endif
         const uint32_t idesc = make_idesc_bf16_f32(TC_M, TCA_ACC_N);
@@ -391,24 +402,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
         for (int64_t st = 0; st < p.n_steps; ++st)
         for (int strm = 0; strm < 2; ++strm) {  // stream = groups strm, strm + 2 (see the sampler warps)
           if (strm >= G) break;
+          const int g = strm + 2 * issuer;      // this issuer's group of the stream (may not exist in a tail round)
+          const bool mine = g < G;
+          if (mine) TC_HOT_WAIT(&a_ready[g], (a_it + (uint32_t)st) & 1);
+          TC_T(9);
+          const uint32_t a_lo = da_lo0 + (uint32_t)g * (TCA_A_BYTES >> 4);
           for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
             const int s = x_it % TCA_STAGES;
-            TC_T(11);
-            mbar_wait(&x_full[s], (x_it / TCA_STAGES) & 1);
+            TC_HOT_WAIT(&x_full[s], (x_it / TCA_STAGES) & 1);
             TC_T(8);
-            for (int g = strm; g < G; g += 2) {
-              if (tile == 0) mbar_wait(&a_ready[g], (a_it + (uint32_t)st) & 1);
-              TC_T(9);
-              const uint32_t a_lo = da_lo0 + (uint32_t)g * (TCA_A_BYTES >> 4);
+            if (mine) {
 #pragma unroll
               for (int h = 0; h < TCA_HALVES; ++h) {  // rows [TCA_ACC_N h, TCA_ACC_N (h + 1)) of the tile -> one accumulator
-                uint32_t& k = strm ? ks1 : ks0;
-                const int b = k & (TCA_NBUF - 1);
-                // TMEM buffer b must be drained by its previous users: this stream's accumulator k - TCA_NBUF and, after
-                // a stream switch, the other stream's last one in this buffer.  uses(s, b) = #{j < k_s : j mod NBUF = b}.
-                const uint32_t u_own = k / TCA_NBUF, u_oth = ((strm ? ks0 : ks1) + (TCA_NBUF - 1) - b) / TCA_NBUF;
-                if (u_own) mbar_wait(&acc_empty[strm * TCA_NBUF + b], (u_own - 1) & 1);
-                if (u_oth) mbar_wait(&acc_empty[(strm ^ 1) * TCA_NBUF + b], (u_oth - 1) & 1);
+                uint32_t& k = strm ? ks1 : ks0;       // accumulators this issuer has issued for the stream
+                const int b = issuer * TCA_NBI + (int)(k % TCA_NBI);
+                // TMEM buffer b must be drained by its previous users: this stream's accumulator k - NBI of this issuer and,
+                // after a stream switch, the other stream's last one in this buffer.  uses(s, b) = #{j < k_s : j mod NBI = b'}.
+                const uint32_t u_own = k / TCA_NBI, u_oth = ((strm ? ks0 : ks1) + (TCA_NBI - 1) - (k % TCA_NBI)) / TCA_NBI;
+                if (u_own) TC_HOT_WAIT(&acc_empty[strm * TCA_NBUF + b], (u_own - 1) & 1);
+                if (u_oth) TC_HOT_WAIT(&acc_empty[(strm ^ 1) * TCA_NBUF + b], (u_oth - 1) & 1);
                 TC_T(10);
                 tc_fence_after();
                 // canonical K-major tile of 256 rows: row group r / 8 is 128 bytes further, so half h starts 16 groups in
@@ -427,20 +439,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
                 ++k;
               }
             }
-            umma_commit(&x_empty[s]);
+            umma_commit(&x_empty[s]);  // (an issuer without a group in this stream arrives at once: the stage needs both)
+            TC_T(11);
           }
         }
       }
       TC_ROUND_END
-    } else if (warp > kMmaWarp) {
+    } else if (warp == kDrawWarp) {
       TC_ROUND_BEGIN
-      // ===== helper warps: the draws of every chain, one step ahead (arwmh.py:162-165,174) =====
-      const int ht = tid - 32 * (kMmaWarp + 1);
+      // ===== draw warp: the draws of every chain, one step ahead (arwmh.py:162-165,174) =====
+      const int ht = lane;
       for (int64_t st = 0; st < p.n_steps; ++st) {
         const int64_t it = p.i0 + st;
         for (int g = 0; g < G; ++g) {
           mbar_wait(&v_empty[g], ((a_it + (uint32_t)st) & 1) ^ 1);
-          for (int row = ht; row < TC_M; row += 32 * TC_HELP_WARPS) {
+          for (int row = ht; row < TC_M; row += 32) {
             const int64_t c = (g0 + g * gs) * TC_M + row;
             const int64_t cc = c < p.C ? c : (p.C - 1);
             float* vrow = sV + (size_t)g * 27 * TC_M + row;
@@ -505,16 +518,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
           // ---- likelihood: sum_n m_n^2 of this stream's groups from the TMEM accumulators (256 columns each)
           for (int tile = 0; tile < p.n_tiles; ++tile) {
 #pragma unroll
-            for (int l = 0; l < 2; ++l) {
+            for (int l = 0; l < 2; ++l) {  // l-th group of the stream <-> issuer l <-> TMEM buffers l * NBI ..
               if (l < n_mine) {
                 float ss = 0.f;
 #pragma unroll 1
                 for (int h = 0; h < TCA_HALVES; ++h) {  // rolled: 128 live accumulator values at a time
-                  const int b = acc_it & (TCA_NBUF - 1);
+                  uint32_t& cnt = l ? acc_it1 : acc_it;
+                  const int b = l * TCA_NBI + (int)(cnt % TCA_NBI);
 #ifdef AMCMC_TC_TIMING
                   const long long td0 = clock64();
 #endif
-                  mbar_wait(&acc_full[half * TCA_NBUF + b], (acc_it / TCA_NBUF) & 1);
+                  TC_HOT_WAIT(&acc_full[half * TCA_NBUF + b], (cnt / TCA_NBI) & 1);
 #ifdef AMCMC_TC_TIMING
                   const long long td1 = clock64();
 #endif
@@ -530,7 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
 #ifdef AMCMC_TC_TIMING
                   if (dbg) { s_dbg[48 + warp * 2] += (unsigned long long)(td1 - td0); s_dbg[49 + warp * 2] += (unsigned long long)(clock64() - td1); }
 #endif
-                  ++acc_it;
+                  ++cnt;
                 }
                 if (l) mine1 += ss; else mine0 += ss;
               }

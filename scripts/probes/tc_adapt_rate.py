@@ -19,7 +19,7 @@ b.set_dense_scale(torch.eye(26) * 0.002)
 for _ in range(2):
     s.run_batch(b, T, collect=())
 torch.cuda.synchronize()
-ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(4)]
+ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(int(os.environ.get('REPS', 4)))]
 for e0, e1 in ev:
     e0.record(); s.run_batch(b, T, collect=()); e1.record()
 torch.cuda.synchronize()
