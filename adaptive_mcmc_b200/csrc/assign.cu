@@ -1,0 +1,284 @@
+// assign.cu -- optimal one-to-one assignment on the GPU for `wasserstein_dist11_p`
+// (reference: python/utils/evaluation.py:42-66, where scipy.optimize.linear_sum_assignment takes 20.7 s for the
+// 10^4 x 10^4 cost matrix of one diamonds run, python/jupyter/posteriordb_diamonds.ipynb:L3342).
+//
+// Algorithm: Bertsekas' forward auction with epsilon-scaling, Jacobi form (every unassigned row bids in every round).
+// Costs are quantised to 24-bit integers c_ij = rint(cost_ij * (2^24 - 1) / max cost) -- the resolution of the float32
+// matrix itself -- and multiplied by (n + 1); with integer prices the final phase (epsilon = 1) then ends within
+// n * epsilon < n + 1 = one cost quantum of the optimum, i.e. AT the optimum of the quantised problem, which is what the
+// tests compare with SciPy's solver on the same integer matrix (equal optimal cost; the matchings may differ in ties).
+//
+// One round = three small kernels (bid / resolve / assign); HBM-bound: a bidding row streams its n int32 costs once
+// (coalesced 16-byte loads) against the n prices, which stay in L2.  No host round trip inside a phase except the
+// unassigned-rows counter, read back every few rounds.
+#include <climits>
+#include <cstring>
+#include <cstdint>
+#include <vector>
+#include "internal.h"
+
+namespace amcmc {
+
+constexpr int kBidThreads = 256;
+constexpr long long kNoBid = LLONG_MIN;
+
+__global__ void assign_max_kernel(const float* __restrict__ c, int64_t total, unsigned int* __restrict__ out_bits) {
+  unsigned int m = 0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const float v = c[k];
+    const unsigned int b = (v > 0.f && v == v) ? __float_as_uint(v) : 0u;  // non-negative floats order like their bit patterns
+    m = b > m ? b : m;
+  }
+  for (int o = 16; o; o >>= 1) { const unsigned int t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, m);
+}
+
+__global__ void assign_quantise_kernel(const float* __restrict__ c, int64_t total, const unsigned int* __restrict__ max_bits,
+                                       int32_t* __restrict__ ci) {
+  const float cmax = __uint_as_float(*max_bits);
+  const double scale = cmax > 0.f ? 16777215.0 / (double)cmax : 0.0;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const float v = c[k];
+    ci[k] = (int32_t)llrint((double)(v > 0.f ? v : 0.f) * scale);
+  }
+}
+
+struct Top2 {
+  long long best, second;
+  int arg;
+};
+__device__ __forceinline__ void top2_push(Top2& t, long long v, int j) {
+  if (v > t.best || (v == t.best && j < t.arg)) { t.second = t.best; t.best = v; t.arg = j; }
+  else if (v > t.second) t.second = v;
+}
+__device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
+  if (b.best > a.best || (b.best == a.best && b.arg < a.arg)) {
+    a.second = a.best > b.second ? a.best : b.second;
+    a.best = b.best; a.arg = b.arg;
+  } else {
+    a.second = a.second > b.best ? a.second : b.best;
+  }
+}
+
+// one block per row; unassigned rows bid for their best column: price + (best - second best value) + eps
+__global__ void __launch_bounds__(kBidThreads)
+auction_bid_kernel(const int32_t* __restrict__ ci, int n, const long long* __restrict__ price, const int* __restrict__ col_of,
+                   long long eps, long long* __restrict__ maxbid, long long* __restrict__ bid_val, int* __restrict__ bid_col) {
+  const int i = blockIdx.x;
+  if (col_of[i] >= 0) return;
+  const long long np1 = (long long)n + 1;
+  const int32_t* row = ci + (int64_t)i * n;
+  Top2 t{kNoBid, kNoBid, INT_MAX};
+  const int n4 = (n % 4 == 0 && (((uintptr_t)row) & 15) == 0) ? n / 4 : 0;
+  for (int q = threadIdx.x; q < n4; q += kBidThreads) {
+    const int4 c4 = reinterpret_cast<const int4*>(row)[q];
+    const int j = 4 * q;
+    top2_push(t, -(long long)c4.x * np1 - price[j], j);
+    top2_push(t, -(long long)c4.y * np1 - price[j + 1], j + 1);
+    top2_push(t, -(long long)c4.z * np1 - price[j + 2], j + 2);
+    top2_push(t, -(long long)c4.w * np1 - price[j + 3], j + 3);
+  }
+  for (int j = 4 * n4 + threadIdx.x; j < n; j += kBidThreads) top2_push(t, -(long long)row[j] * np1 - price[j], j);
+  for (int o = 16; o; o >>= 1) {
+    Top2 u;
+    u.best = __shfl_xor_sync(0xffffffffu, t.best, o);
+    u.second = __shfl_xor_sync(0xffffffffu, t.second, o);
+    u.arg = __shfl_xor_sync(0xffffffffu, t.arg, o);
+    top2_merge(t, u);
+  }
+  __shared__ Top2 sh[kBidThreads / 32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kBidThreads / 32; ++w) top2_merge(t, sh[w]);
+    const long long gap = t.second == kNoBid ? 0 : t.best - t.second;  // n == 1: no competitor
+    const long long bid = price[t.arg] + gap + eps;
+    bid_val[i] = bid;
+    bid_col[i] = t.arg;
+    atomicMax(&maxbid[t.arg], bid);
+  }
+}
+
+// the highest bid of a column wins; among equal bids the lowest row index
+__global__ void auction_resolve_kernel(int n, const int* __restrict__ col_of, const long long* __restrict__ maxbid,
+                                       const long long* __restrict__ bid_val, const int* __restrict__ bid_col, int* __restrict__ winner) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || col_of[i] >= 0) return;
+  const int j = bid_col[i];
+  if (bid_val[i] == maxbid[j]) atomicMin(&winner[j], i);
+}
+
+__global__ void auction_assign_kernel(int n, int* __restrict__ col_of, int* __restrict__ row_of, long long* __restrict__ price,
+                                      long long* __restrict__ maxbid, int* __restrict__ winner, int* __restrict__ n_unassigned) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int w = winner[j];
+  if (w == INT_MAX) return;
+  const int prev = row_of[j];
+  if (prev >= 0) col_of[prev] = -1;       // the previous owner is outbid (it did not bid this round: it was assigned)
+  else atomicSub(n_unassigned, 1);
+  row_of[j] = w;
+  col_of[w] = j;
+  price[j] = maxbid[j];
+  maxbid[j] = kNoBid;
+  winner[j] = INT_MAX;
+}
+
+// Tail of a phase: once only a few rows are unassigned a Jacobi round is three kernel launches for one or two bids (93 % of
+// all rounds at n = 2000 have at most 8 unassigned rows).  One CTA then finishes the phase in Gauss-Seidel order: pop an
+// unassigned row, scan its n values with all threads, bid, assign at once, push the evicted owner -- ~2 us per bid
+// instead of ~20 us per round.  The queue holds at most kTailQueue rows (the number of unassigned rows never grows).
+constexpr int kTailThreads = 1024;
+constexpr int kTailQueue = 256;
+
+__global__ void __launch_bounds__(kTailThreads)
+auction_tail_kernel(const int32_t* __restrict__ ci, int n, volatile long long* price, volatile int* col_of, volatile int* row_of,
+                    long long eps, int* __restrict__ n_unassigned, long long max_bids, unsigned long long* __restrict__ bids_done) {
+  __shared__ int queue[kTailQueue];
+  __shared__ int q_count;
+  __shared__ Top2 sh[kTailThreads / 32];
+  if (threadIdx.x == 0) q_count = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kTailThreads)
+    if (col_of[i] < 0) {
+      const int k = atomicAdd(&q_count, 1);
+      if (k < kTailQueue) queue[k] = i;
+    }
+  __syncthreads();
+  if (q_count > kTailQueue) return;  // too many for the tail: the caller goes on with Jacobi rounds
+  const long long np1 = (long long)n + 1;
+  long long done = 0;
+  while (q_count > 0 && done < max_bids) {
+    const int i = queue[q_count - 1];
+    const int32_t* row = ci + (int64_t)i * n;
+    Top2 t{kNoBid, kNoBid, INT_MAX};
+    for (int j = threadIdx.x; j < n; j += kTailThreads) top2_push(t, -(long long)__ldg(row + j) * np1 - price[j], j);
+    for (int o = 16; o; o >>= 1) {
+      Top2 u;
+      u.best = __shfl_xor_sync(0xffffffffu, t.best, o);
+      u.second = __shfl_xor_sync(0xffffffffu, t.second, o);
+      u.arg = __shfl_xor_sync(0xffffffffu, t.arg, o);
+      top2_merge(t, u);
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kTailThreads / 32; ++w) top2_merge(t, sh[w]);
+      const long long gap = t.second == kNoBid ? 0 : t.best - t.second;
+      const int j = t.arg;
+      const int prev = row_of[j];
+      price[j] = price[j] + gap + eps;
+      row_of[j] = i;
+      col_of[i] = j;
+      if (prev >= 0) { col_of[prev] = -1; queue[q_count - 1] = prev; }  // the evicted owner takes the slot of the popped row
+      else { q_count = q_count - 1; atomicSub(n_unassigned, 1); }
+      __threadfence_block();
+    }
+    ++done;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(bids_done, (unsigned long long)done);
+}
+
+__global__ void auction_reset_kernel(int n, int* __restrict__ col_of, int* __restrict__ row_of, long long* __restrict__ maxbid,
+                                     int* __restrict__ winner, int* __restrict__ n_unassigned) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) *n_unassigned = n;
+  if (k >= n) return;
+  col_of[k] = -1; row_of[k] = -1; maxbid[k] = kNoBid; winner[k] = INT_MAX;
+}
+
+__global__ void assign_total_kernel(const int32_t* __restrict__ ci, const float* __restrict__ c, int n, const int* __restrict__ col_of,
+                                    unsigned long long* __restrict__ total_int, double* __restrict__ total_float) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long vi = 0;
+  double vf = 0.0;
+  if (i < n) {
+    const int j = col_of[i];
+    vi = (unsigned long long)ci[(int64_t)i * n + j];
+    vf = (double)c[(int64_t)i * n + j];
+  }
+  for (int o = 16; o; o >>= 1) { vi += __shfl_xor_sync(0xffffffffu, vi, o); vf += __shfl_xor_sync(0xffffffffu, vf, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(total_int, vi); atomicAdd(total_float, vf); }
+}
+
+}  // namespace amcmc
+
+using namespace amcmc;
+
+// Optimal assignment of the n x n float32 cost matrix `cost` (device, row-major).  Outputs (all optional except col_of_row):
+//   col_of_row   [n] int32 (device): column matched to every row
+//   quantised    [n*n] int32 (device) or NULL: the integer matrix that was solved (for the parity tests)
+//   out_host[3]  : sum of the float costs of the matching, sum of the quantised costs, number of auction rounds
+extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* col_of_row, int32_t* quantised, double* out_host,
+                                     void* stream) {
+  if (!cost || !col_of_row || n64 < 1 || n64 > 46000) { set_error("amcmc_eval_assignment: need 1 <= n <= 46000"); return AMCMC_ERR_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = (int)n64;
+  const int64_t total = (int64_t)n * n;
+  int rc;
+  char* buf = nullptr;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_ci = quantised ? 0 : al((size_t)total * 4);
+  const size_t bytes = b_ci + 3 * al((size_t)n * 8) + 4 * al((size_t)n * 4) + 256;
+  if ((rc = check_cuda(cudaMalloc(&buf, bytes), "cudaMalloc(assignment workspace)"))) return rc;
+  char* p = buf;
+  auto take = [&](size_t b) { char* q = p; p += al(b); return (void*)q; };
+  int32_t* ci = quantised ? quantised : (int32_t*)take((size_t)total * 4);
+  long long* price = (long long*)take((size_t)n * 8);
+  long long* maxbid = (long long*)take((size_t)n * 8);
+  long long* bid_val = (long long*)take((size_t)n * 8);
+  int* row_of = (int*)take((size_t)n * 4);
+  int* winner = (int*)take((size_t)n * 4);
+  int* bid_col = (int*)take((size_t)n * 4);
+  int* col_of = (int*)col_of_row;
+  unsigned int* scal = (unsigned int*)take(64);  // [0] max bits, [2] unassigned counter, [4..5] int total, [6..7] float total
+  int* n_un = (int*)(scal + 2);
+  cudaMemsetAsync(scal, 0, 64, s);
+  cudaMemsetAsync(price, 0, (size_t)n * 8, s);
+  const int gs = 148 * 8;
+  assign_max_kernel<<<gs, 256, 0, s>>>(cost, total, scal);
+  assign_quantise_kernel<<<gs, 256, 0, s>>>(cost, total, scal, ci);
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  // epsilon-scaling on costs multiplied by (n + 1): start at ~1/8 of the largest scaled cost, divide by 6 down to 1
+  long long eps = ((long long)16777215 * (n + 1)) / 8;
+  if (eps < 1) eps = 1;
+  long rounds = 0, host_iters = 0;
+  unsigned long long* tail_bids = (unsigned long long*)(scal + 8);
+  for (;;) {
+    auction_reset_kernel<<<nb, 256, 0, s>>>(n, col_of, row_of, maxbid, winner, n_un);
+    int un = n;
+    while (un > 0) {
+      if (un <= kTailQueue / 2) {  // few rows left: finish the phase in one CTA (Gauss-Seidel order)
+        auction_tail_kernel<<<1, kTailThreads, 0, s>>>(ci, n, price, col_of, row_of, eps, n_un, (long long)1 << 22, tail_bids);
+      } else {
+        for (int r = 0; r < 4; ++r) {
+          auction_bid_kernel<<<n, kBidThreads, 0, s>>>(ci, n, price, col_of, eps, maxbid, bid_val, bid_col);
+          auction_resolve_kernel<<<nb, 256, 0, s>>>(n, col_of, maxbid, bid_val, bid_col, winner);
+          auction_assign_kernel<<<nb, 256, 0, s>>>(n, col_of, row_of, price, maxbid, winner, n_un);
+        }
+        rounds += 4;
+      }
+      if ((rc = check_cuda(cudaMemcpyAsync(&un, n_un, 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync"))) { cudaFree(buf); return rc; }
+      if ((rc = check_cuda(cudaStreamSynchronize(s), "auction round"))) { cudaFree(buf); return rc; }
+      if (++host_iters > 2000000) { cudaFree(buf); set_error("amcmc_eval_assignment: auction did not terminate"); return AMCMC_ERR_CUDA; }
+    }
+    if (eps == 1) break;
+    eps /= 6;
+    if (eps < 1) eps = 1;
+  }
+  if (out_host) {
+    assign_total_kernel<<<nb, 256, 0, s>>>(ci, cost, n, col_of, (unsigned long long*)(scal + 4), (double*)(scal + 6));
+    unsigned int h[8];
+    if ((rc = check_cuda(cudaMemcpyAsync(h, scal, 32, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync"))) { cudaFree(buf); return rc; }
+    if ((rc = check_cuda(cudaStreamSynchronize(s), "assignment totals"))) { cudaFree(buf); return rc; }
+    unsigned long long ti; double tf;
+    memcpy(&ti, h + 4, 8); memcpy(&tf, h + 6, 8);
+    unsigned long long tb = 0;
+    cudaMemcpy(&tb, tail_bids, 8, cudaMemcpyDeviceToHost);
+    out_host[0] = tf; out_host[1] = (double)ti; out_host[2] = (double)rounds + (double)tb;  // Jacobi rounds + Gauss-Seidel bids
+  }
+  rc = check_cuda(cudaGetLastError(), "amcmc_eval_assignment");
+  cudaFree(buf);
+  return rc;
+}

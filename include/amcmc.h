@@ -212,6 +212,13 @@ int amcmc_eval_cost_matrix(const float* x, int64_t n, const float* y, int64_t m,
                            void* stream);
 /* out_host[k] = mean_i x_ik^p, k < d: the moment estimates of pth_moment_rmse (evaluation.py:33-34). */
 int amcmc_eval_moment(const float* x, int64_t n, int d, double p, double* out_host, void* stream);
+/* scipy.optimize.linear_sum_assignment(cost_matrix) of wasserstein_dist11_p (evaluation.py:59) for a square n x n float32
+ * DEVICE cost matrix: forward auction with epsilon-scaling on the costs quantised to 24-bit integers
+ * c_ij = rint(cost_ij * (2^24 - 1) / max cost) (optimal for the quantised matrix; equal optimal cost as SciPy on it).
+ * col_of_row [n] int32 DEVICE: the column matched to every row.  quantised: DEVICE [n*n] int32 or NULL, receives the
+ * integer matrix.  out_host[3] (HOST, optional): sum of the float costs of the matching, sum of the integer costs,
+ * auction rounds.  Synchronises `stream`. */
+int amcmc_eval_assignment(const float* cost, int64_t n, int32_t* col_of_row, int32_t* quantised, double* out_host, void* stream);
 
 const char* amcmc_last_error(void);
 int amcmc_version(void);

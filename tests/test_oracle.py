@@ -251,3 +251,22 @@ def test_evaluation_oracle_identities():
     # the 1-1 coupling of a sample with a shifted copy of itself costs exactly the shift
     assert abs(oe.wasserstein_dist11_p(x[:60], x[:60] + np.float32(0.25), 2.0) - 0.25 * np.sqrt(5)) < 1e-5
     assert abs(oe.pth_moment_rmse(x, x, 2.0)) == 0.0
+
+
+def test_auction_restatement_matches_scipy():
+    """oracle/assignment_numpy.py (the algorithm of csrc/assign.cu) ends at SciPy's optimum on the integer-scaled costs."""
+    from scipy.optimize import linear_sum_assignment
+
+    from oracle import assignment_numpy as oa
+
+    rng = np.random.default_rng(4)
+    for n, d in ((1, 2), (2, 2), (9, 3), (80, 6), (250, 26)):
+        x, y = rng.normal(size=(n, d)), rng.normal(size=(n, d)) + 0.2
+        ci = oa.quantise(np.linalg.norm(x[:, None] - y[None], axis=-1).astype(np.float32))
+        col, _ = oa.auction(ci)
+        ri, cj = linear_sum_assignment(ci)
+        assert sorted(col.tolist()) == list(range(n)) and ci[np.arange(n), col].sum() == ci[ri, cj].sum()
+    ci = oa.quantise(rng.integers(0, 3, size=(40, 40)).astype(np.float32))
+    col, _ = oa.auction(ci)
+    ri, cj = linear_sum_assignment(ci)
+    assert ci[np.arange(40), col].sum() == ci[ri, cj].sum()
