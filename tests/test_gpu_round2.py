@@ -194,3 +194,22 @@ def test_sample_Pnx_diamonds_runs_on_tensor_cores():
     assert 0.3 < float(moved.float().mean()) <= 1.0
     close = ((a - b).abs().amax(-1) < 2e-5).float().mean()
     assert float(close) > 0.95, float(close)
+
+
+def test_torch_custom_ops_wrap_the_c_abi():
+    """SURVEY 8b: `amcmc::arwmh_run` / `amcmc::logdensity` registered as torch operators over the same C entry points."""
+    import adaptive_mcmc_b200.torch_ops  # noqa: F401  (registers torch.ops.amcmc.*)
+
+    Cn, T = 512, 200
+    s = am.ARWMH(models.eight_schools, num_chains=Cn)
+    st = s.init(6, num_warmup=50, init_params=None)
+    b1 = am.ChainBatch.from_state(s.potential, st)
+    b2 = am.ChainBatch.from_state(s.potential, st)
+    raw = s.run_batch(b1, T, thinning=10)
+    h = s.potential.handle.value if hasattr(s.potential.handle, "value") else int(s.potential.handle)
+    U = torch.ops.amcmc.logdensity(h, b2.z)
+    torch.testing.assert_close(U, b2.pe, rtol=1e-6, atol=1e-5)
+    oz, ope = torch.ops.amcmc.arwmh_run(h, b2.z, b2.pe, b2.macc, b2.loc, b2.scale, b2.lam, b2.asc, 0, T, 10, 0, 50, 2 / 3, 0.234, 1e-6,
+                                        True, b2.seed, b2.chain_offset, _lib.KERNEL_ARWMH, _lib.IMPL_AUTO)
+    assert torch.equal(oz, raw["z"]) and torch.equal(ope, raw["potential_energy"])
+    assert torch.equal(b1.z, b2.z) and torch.equal(b1.scale, b2.scale) and torch.equal(b1.lam, b2.lam)
