@@ -367,7 +367,7 @@ def run_ours(args):
             "copy_probe": probe_copies(dev, world, local, quick=True),
         }
         S_ = T // args.thinning
-        chunk_S = min(S_, (2048 + args.thinning - 1) // args.thinning) or 1
+        chunk_S = min(S_, (512 + args.thinning - 1) // args.thinning) or 1
         launches += K * max(1, -(-S_ // chunk_S))
 
     extra = None
