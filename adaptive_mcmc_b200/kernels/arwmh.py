@@ -84,6 +84,7 @@ class ChainBatch:
         self.i = 0
         self.seed = int(seed)
         self.chain_offset = int(chain_offset)
+        self.jax_keys = None  # int32 [2, C] holding the uint32 words of every chain's JAX key (rng = "jax")
         if alloc:
             kw = dict(dtype=potential.dtype, device=potential.device)
             self.z = torch.empty(self.d, self.C, **kw)
@@ -99,6 +100,7 @@ class ChainBatch:
     def clone(self):
         b = ChainBatch(self.potential, self.C, self.seed, self.chain_offset, alloc=False)
         b.i = self.i
+        b.jax_keys = None if self.jax_keys is None else self.jax_keys.clone()
         for f in self._FIELDS:
             setattr(b, f, getattr(self, f).clone())
         return b
@@ -140,7 +142,10 @@ class ChainBatch:
         pot = self.potential
         z = pot.unravel(self.z.t())
         adapt = ARWMHAdaptState(self.loc.t(), self.dense_scale(), self.lam)
-        key = torch.tensor([self.seed, self.chain_offset], dtype=torch.int64)
+        if self.jax_keys is not None:  # rng = "jax": ARWMHState.rng_key is every chain's current JAX key, uint32 words [C, 2]
+            key = self.jax_keys.t().to(torch.int64) & 0xFFFFFFFF
+        else:
+            key = torch.tensor([self.seed, self.chain_offset], dtype=torch.int64)
         st = ARWMHState(self.i, z, self.pe, self.macc, adapt, self.asc, key)
         st._batch = self
         return st
@@ -152,8 +157,13 @@ class ChainBatch:
             return b.clone() if copy else b
         zf = potential.ravel(state.z)
         C_ = zf.shape[0]
-        key = np.asarray(state.rng_key).ravel() if state.rng_key is not None else np.array([0, 0])
-        b = ChainBatch(potential, C_, int(key[0]), int(key[1]) if key.size > 1 else 0)
+        rk = state.rng_key.cpu().numpy() if isinstance(state.rng_key, torch.Tensor) else (np.asarray(state.rng_key) if state.rng_key is not None else np.array([0, 0]))
+        if rk.ndim == 2 and rk.shape == (C_, 2) and C_ != 1:  # per-chain JAX keys (rng = "jax")
+            b = ChainBatch(potential, C_, 0, 0)
+            b.jax_keys = torch.from_numpy(np.ascontiguousarray(rk.astype(np.uint64).astype(np.uint32).T).view(np.int32)).to(potential.device)
+        else:
+            key = rk.ravel()
+            b = ChainBatch(potential, C_, int(key[0]), int(key[1]) if key.size > 1 else 0)
         b.i = int(state.i)
         kw = dict(dtype=potential.dtype, device=potential.device)
 
@@ -200,6 +210,7 @@ class ARWMH:
         dtype=torch.float32,
         device=None,
         chain_offset=0,
+        rng="philox",
     ):
         # arwmh.py:69-70
         if not (model is None) ^ (potential_fn is None):
@@ -226,6 +237,13 @@ class ARWMH:
         self._chain_offset = int(chain_offset)
         self._bound_key = None
         self.impl = _lib.IMPL_AUTO
+        # rng = "philox": in-kernel counter RNG keyed by (seed, global chain id, iteration) -- the fast path.
+        # rng = "jax": the reference's own stream (jax.random threefry2x32; arwmh.py:162-165,174): every chain carries a JAX
+        # key, its draws are generated on the GPU (amcmc_jax_draws) and consumed through the external-draws mode, so a run
+        # started from `PRNGKey(seed)` and the reference's initial position replays the reference's trajectory.
+        if rng not in ("philox", "jax"):
+            raise ValueError("rng must be 'philox' or 'jax'")
+        self._rng = rng
 
     @property
     def model(self):
@@ -290,6 +308,11 @@ class ARWMH:
             )
         _lib.check(rc, "amcmc_arwmh_init")
         batch.i = 0
+        if self._rng == "jax":
+            from ..utils import jax_prng
+
+            keys = jax_prng.chain_keys(rng_key.cpu().numpy() if isinstance(rng_key, torch.Tensor) else rng_key, C_)  # [C, 2]
+            batch.jax_keys = torch.from_numpy(np.ascontiguousarray(keys.T).view(np.int32)).to(pot.device)
         return self._state_from_batch(batch)
 
     # ---- the fused run ----------------------------------------------------------
@@ -316,6 +339,20 @@ class ARWMH:
         a.chain_offset = batch.chain_offset
         a.kernel_kind = kernel_kind
         a.impl = self.impl
+        if draws is None and self._rng == "jax" and kernel_kind != _lib.KERNEL_ASSS and T > 0:
+            if batch.jax_keys is None:
+                raise ValueError("rng='jax' needs a state made by init() of this sampler (it carries the chains' JAX keys)")
+            n_bytes = T * (batch.d + 1) * batch.C * (4 if pot.dtype == torch.float32 else 8)
+            if n_bytes > (32 << 30):
+                raise ValueError(f"rng='jax' stages all draws of a call in HBM ({n_bytes / 2**30:.0f} GiB here): call run in pieces")
+            nrm = torch.empty(T, batch.d, batch.C, **kw)
+            uni = torch.empty(T, batch.C, **kw)
+            with torch.cuda.device(pot.device):
+                _lib.check(_lib.lib().amcmc_jax_draws(batch.jax_keys.data_ptr(), batch.C, batch.d, T,
+                                                      _lib.AMCMC_F32 if pot.dtype == torch.float32 else _lib.AMCMC_F64,
+                                                      nrm.data_ptr(), uni.data_ptr(),
+                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "amcmc_jax_draws")
+            draws = (nrm, uni)
         if draws is not None:
             nrm, uni = draws
             nrm = torch.as_tensor(nrm, **kw).contiguous()

@@ -220,6 +220,13 @@ int amcmc_eval_moment(const float* x, int64_t n, int d, double p, double* out_ho
  * auction rounds.  Synchronises `stream`. */
 int amcmc_eval_assignment(const float* cost, int64_t n, int32_t* col_of_row, int32_t* quantised, double* out_host, void* stream);
 
+/* The reference's random stream on the GPU (python/kernels/arwmh.py:162-165,174: split(rng_key, 3), Normal().sample,
+ * Uniform().sample with jax's threefry2x32 PRNG): for every chain, n_steps steps of draws from its JAX key, written in the
+ * external-draws layout of amcmc_arwmh_run (normals[n_steps][dim][C], uniforms[n_steps][C], `dtype` elements holding float32
+ * values).  keys: DEVICE uint32 [2][C], replaced by the keys after n_steps steps (ARWMHState.rng_key).  Asynchronous. */
+int amcmc_jax_draws(uint32_t* keys, int64_t n_chains, int dim, int64_t n_steps, int dtype, void* normals, void* uniforms,
+                    void* stream);
+
 const char* amcmc_last_error(void);
 int amcmc_version(void);
 
