@@ -92,3 +92,13 @@ def test_cuda_kernels_follow_the_exported_trajectories(tmp_path):
         err = (np.abs(zg - d["z"]) / (1 + np.abs(d["z"]))).max(axis=(0, 2))
         assert err[same].max() < 1e-3, err[same].max()
         np.testing.assert_allclose(last.adapt_state.scale.cpu().numpy()[same], d["scale"][same], rtol=3e-3, atol=3e-3)
+        # ... and from the seeds alone: rng="jax" regenerates the reference's stream on the GPU (every exported chain is a
+        # single-chain run under PRNGKey(seed), run_eight_schools_lr_decay.py:44-46), only q0 comes from the file
+        keys = np.stack([jr.prng_key(int(sd)) for sd in d["seeds"]])
+        s2 = am.ARWMH(models.eight_schools, num_chains=S, rng="jax", init_strategy=am.init_to_value(torch.from_numpy(d["q0"])))
+        st2 = s2.init(keys, num_warmup=int(d["num_warmup"]), init_params=None)
+        coll2, _ = s2.run(st2, T, record_accept=True)
+        same2 = (coll2["accept"].cpu().numpy() == d["accept"]).all(axis=0)
+        assert same2.mean() >= 0.85, same2.mean()
+        zg2 = np.concatenate([v.cpu().numpy().reshape(T, S, -1) for v in coll2["z"].values()], axis=-1)
+        assert (np.abs(zg2 - d["z"]) / (1 + np.abs(d["z"]))).max(axis=(0, 2))[same2].max() < 1e-3
