@@ -257,6 +257,27 @@ def synthetic_diamonds(n=5000, k=25, seed=0, sigma=0.123):
     return dict(X=X, Y=Y)
 
 
+def diamonds_from_sufficient_stats(n, G, h, yy, seed=0, col_means=None):
+    """A diamonds-shaped data set (X [n, K] with column 0 = ones, Y [n]) with the given sufficient statistics of the Gaussian
+    linear likelihood: G = X1^T X1, h = X1^T Y, yy = Y^T Y for X1 = [1 | centred predictors] (python/scripts/run_diamonds_lr_decay.py:
+    24-40 depends on the data through these only).  Xc = Q R with Q orthonormal and orthogonal to the ones vector, R^T R = G[1:,1:];
+    Y = mean + Xc b_ols + r with r orthogonal to [1, Q] and |r|^2 = the residual sum of squares.  Used with the statistics recovered
+    from the posteriordb reference draws the reference ships (tests/golden/reference_pins.json:diamonds_recovered_stats)."""
+    G = np.asarray(G, np.float64)
+    h = np.asarray(h, np.float64)
+    k = G.shape[0]
+    rng = np.random.default_rng(seed)
+    Q, _ = np.linalg.qr(np.column_stack([np.ones(n), rng.normal(size=(n, k))]))
+    R = np.linalg.cholesky(G[1:, 1:]).T
+    Xc = Q[:, 1:k] @ R
+    beta = np.linalg.solve(G, h)
+    rss0 = float(yy) - h @ beta
+    Y = beta[0] + Xc @ beta[1:] + np.sqrt(max(rss0, 0.0)) * Q[:, k]
+    if col_means is None:
+        col_means = np.linspace(0.2, 1.5, k - 1)
+    return dict(X=np.column_stack([np.ones(n), Xc + np.asarray(col_means)[None, :]]), Y=Y)
+
+
 def synthetic_kidiq(n=434, seed=0):
     rng = np.random.default_rng(seed)
     mom_hs = (rng.random(n) < 0.79).astype(np.float64)

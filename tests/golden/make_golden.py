@@ -76,6 +76,9 @@ def main():
             # identified coefficients only through the N(0,1) prior of b)
             "corr_logsigma_beta": np.corrcoef(np.column_stack([x[:, 25], x[:, :25]]).T)[0, 1:].tolist(),
         }
+        # the draws themselves (float32, 10000 x 26 in the eval_diamonds.py:78-87 order): the `y` of the reference's quality
+        # metrics (eval_diamonds.py:62-74, 100-104), needed by scripts/eval_diamonds.py / tests/test_gpu_quality.py on the GPU box
+        np.savez_compressed(os.path.join(HERE, "diamonds_reference_draws.npz"), y=x.astype(np.float32))
         # (5) a diamonds-equivalent data set: the Gaussian-linear likelihood depends on the data only through
         #     (N, Xc^T Xc, Xc^T Y, sum Y, Y^T Y); recover them from the draws' mean / covariance / E[sigma^2]
         #     (oracle/diamonds_exact.py) -- posteriordb's diamonds.json itself is not in the image.
