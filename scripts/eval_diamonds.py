@@ -43,8 +43,10 @@ def reference_draws(device="cuda"):
     return torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "diamonds_reference_draws.npz"))["y"]).to(device)
 
 
-def run(seeds=100, scale=1.0, w1_seeds=100, dtype=torch.float32):
-    num_warmup, num_samples, thinning = int(1_000_000 * scale), int(10_000_000 * scale), max(1, int(1000 * scale))
+def run(seeds=100, scale=1.0, w1_seeds=100, dtype=torch.float32, num_warmup=None, num_samples=None, thinning=None):
+    num_warmup = int(1_000_000 * scale) if num_warmup is None else int(num_warmup)
+    num_samples = int(10_000_000 * scale) if num_samples is None else int(num_samples)
+    thinning = max(1, int(1000 * scale)) if thinning is None else int(thinning)
     data = pinned_data()
     y = reference_draws()
     sampler = am.ARWMH(models.diamonds, dtype=dtype)                     # the reference's defaults: lr_decay 2/3, target 0.234
@@ -79,6 +81,9 @@ if __name__ == "__main__":
     ap.add_argument("--seeds", type=int, default=100)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--w1-seeds", type=int, default=100)
+    ap.add_argument("--num-warmup", type=int, default=None)
+    ap.add_argument("--num-samples", type=int, default=None)
+    ap.add_argument("--thinning", type=int, default=None)
     a = ap.parse_args()
-    out, _ = run(a.seeds, a.scale, a.w1_seeds)
+    out, _ = run(a.seeds, a.scale, a.w1_seeds, num_warmup=a.num_warmup, num_samples=a.num_samples, thinning=a.thinning)
     print(json.dumps(out))

@@ -69,3 +69,31 @@ def test_eight_schools_quality_table():
     assert abs(w_s - rec["wasserstein"][0]) < 0.015, w_s
     # ---- and the ordering the reference reports between the two samplers
     assert mmd.mean() > mmd_s.mean() and rmse.mean() > rmse_s.mean() and w < w_s
+
+
+@pytest.mark.gpu
+def test_diamonds_quality_table():
+    """The reference's 100-seed quality experiment for diamonds (run_diamonds_wasserstein.py + eval_diamonds.py): 100 seeds as
+    100 chains of one launch on the CTA-per-chain kernel, from the reference's own start (q0 ~ U(-2,2)^26, identity factor),
+    metrics against the reference's own y -- the posteriordb draws it ships -- on the diamonds-equivalent data set recovered
+    from them (tests/test_diamonds_pin.py).  Recorded (posteriordb_diamonds.ipynb:L3635, mean +- sd over 100 seeds):
+    rmse_means 0.01566 +- 0.0074, wasserstein 0.12315 +- 0.00126, mmd 0.03310 +- 0.00346.
+
+    Run length: the committed script says 10^6 warm-up + 10^7 samples, thinning 1000 (run_diamonds_wasserstein.py:67); with that
+    the GPU run is BETTER than the recorded table in all three metrics (0.0062 / 0.12049 / 0.0151, at the NUTS / ASSS floor the
+    reference records: 0.0107 / 0.12183 / 0.0142).  The recorded table is reproduced -- means AND seed-to-seed spreads -- by
+    10^6 warm-up + 10^6 samples, thinning 100 (measured: 0.01501 +- 0.00707 / 0.12327 +- 0.00115 / 0.03255 +- 0.00328), which is
+    evidently what produced it (the committed script cannot run as it is: SURVEY section 3.1).  That configuration is the test."""
+    from eval_diamonds import RECORDED, run
+
+    out, rows = run(seeds=100, w1_seeds=12, num_warmup=1_000_000, num_samples=1_000_000, thinning=100)
+    print(json.dumps(out))
+    assert abs(out["accept"] - 0.234) < 0.01
+    r = out["rmse_means"]
+    assert abs(r["mean"] - RECORDED["rmse_means"][0]) < 3 * (RECORDED["rmse_means"][1] + r["sd"]) / 10, r   # 3 SE of both means
+    assert 0.6 * RECORDED["rmse_means"][1] < r["sd"] < 1.6 * RECORDED["rmse_means"][1], r
+    m = out["mmd"]
+    assert abs(m["mean"] - RECORDED["mmd"][0]) < 3 * (RECORDED["mmd"][1] + m["sd"]) / 10, m
+    assert 0.6 * RECORDED["mmd"][1] < m["sd"] < 1.6 * RECORDED["mmd"][1], m
+    w = out["wasserstein"]
+    assert abs(w["mean"] - RECORDED["wasserstein"][0]) < 3 * RECORDED["wasserstein"][1] / np.sqrt(12) + 3 * RECORDED["wasserstein"][1] / 10, w
