@@ -275,7 +275,11 @@ class ARWMH:
         self._num_warmup = int(num_warmup)
         self._bind(tuple(model_args), model_kwargs)
         pot = self._potential_fn
-        seed = _parse_key(rng_key)
+        if self._rng == "jax":  # an int seed, one key, or per-chain keys [C, 2]; the Philox seed (q0 draws only) is the first key
+            seed = _parse_key(np.asarray(rng_key.cpu() if isinstance(rng_key, torch.Tensor) else rng_key).reshape(-1)[:2]
+                              if not isinstance(rng_key, (int, np.integer)) else rng_key)
+        else:
+            seed = _parse_key(rng_key)
         use_given = 0
         radius = 2.0
         zf = None

@@ -51,7 +51,7 @@ def test_eight_schools_quality_table():
         assert x.shape == (100, 10000, 10)
         rmse = np.array([ev.pth_moment_rmse(x[k].contiguous(), y, p=1) for k in range(100)])
         mmd = np.array([ev.mmd_heuristic(x[k].contiguous(), y) for k in range(100)])
-        w = ev.wasserstein_dist11_p(x[0].contiguous(), y)  # the 10^4 x 10^4 assignment (20 s of host time): one seed
+        w = float(np.mean([ev.wasserstein_dist11_p(x[k].contiguous(), y) for k in range(8)]))  # 10^4 x 10^4 assignments on the GPU
         res[name] = (rmse, mmd, w)
     # ---- ARWMH: recorded 0.0745 +- 0.0177 / 1.6865 +- 0.0028 / 0.01569 +- 0.00112 (mean +- sd over 100 seeds)
     rmse, mmd, w = res["arwm"]
