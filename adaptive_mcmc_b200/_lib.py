@@ -103,6 +103,7 @@ EXPORTED_SYMBOLS = (
     "amcmc_eval_cost_matrix",
     "amcmc_eval_moment",
     "amcmc_eval_assignment",
+    "amcmc_eval_sinkhorn",
     "amcmc_jax_draws",
     "amcmc_last_error",
     "amcmc_version",
@@ -166,6 +167,9 @@ def lib():
     L.amcmc_eval_cost_matrix.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
     L.amcmc_eval_moment.restype = C.c_int
     L.amcmc_eval_moment.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_void_p]
+    L.amcmc_eval_sinkhorn.restype = C.c_int
+    L.amcmc_eval_sinkhorn.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
     L.amcmc_jax_draws.restype = C.c_int
     L.amcmc_jax_draws.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.amcmc_eval_assignment.restype = C.c_int

@@ -220,6 +220,14 @@ int amcmc_eval_moment(const float* x, int64_t n, int d, double p, double* out_ho
  * auction rounds.  Synchronises `stream`. */
 int amcmc_eval_assignment(const float* cost, int64_t n, int32_t* col_of_row, int32_t* quantised, double* out_host, void* stream);
 
+/* wasserstein_sinkhorn (evaluation.py:69-97: OTT-JAX linear.solve on a PointCloud, `ot.ent_reg_cost`) for two uniform samples:
+ * log-domain Sinkhorn on the DEVICE float32 cost matrix [n][m].  epsilon <= 0 selects 0.05 x mean cost.  threshold: L1 error of
+ * the row marginal, checked every `inner_iterations`; at most `max_iterations` (OTT defaults as recalled: 1e-3, 10, 2000).
+ * out_host[5] (HOST): ent_reg_cost = sum a f + sum b g + eps (1 - sum P), iterations, last marginal error, converged, epsilon.
+ * f_out / g_out: optional DEVICE potentials [n] / [m].  Synchronises `stream`. */
+int amcmc_eval_sinkhorn(const float* cost, int64_t n, int64_t m, double epsilon, double threshold, int max_iterations,
+                        int inner_iterations, float* f_out, float* g_out, double* out_host, void* stream);
+
 /* The reference's random stream on the GPU (python/kernels/arwmh.py:162-165,174: split(rng_key, 3), Normal().sample,
  * Uniform().sample with jax's threefry2x32 PRNG): for every chain, n_steps steps of draws from its JAX key, written in the
  * external-draws layout of amcmc_arwmh_run (normals[n_steps][dim][C], uniforms[n_steps][C], `dtype` elements holding float32

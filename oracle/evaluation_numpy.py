@@ -77,3 +77,35 @@ def max_sliced_wasserstein_given_directions(mu, nu, directions, p=1.0):
     """evaluation.py:185-198 with the directions supplied (the reference draws them with jax.random.normal)."""
     directions = directions / np.linalg.norm(directions, axis=1, keepdims=True)
     return float(max(wasserstein_1d(mu @ dd, nu @ dd, p) for dd in directions))
+
+
+def wasserstein_sinkhorn(u, v, epsilon=None, threshold=1e-3, max_iterations=2000, inner_iterations=10, return_info=False):
+    """python/utils/evaluation.py:69-97 restated without OTT-JAX (a third-party dependency of the reference, not installable
+    here): log-domain Sinkhorn in float64 for uniform weights and the Euclidean cost, with the defaults of
+    `ott.solvers.linear.sinkhorn.Sinkhorn` as recalled (zero initial potentials; one iteration = g-update then f-update; the L1
+    error of the row marginal is checked every `inner_iterations`; epsilon = 0.05 x mean cost when None) and OTT's
+    `ent_reg_cost` of a balanced problem, sum a f + sum b g + eps (1 - sum P).  PARITY STATUS: unpinned against OTT."""
+    from scipy.special import logsumexp
+
+    Cm = distance_matrix(u, v, 2.0).astype(np.float32).astype(np.float64)  # the GPU solves the float32 matrix
+    n, m = Cm.shape
+    eps = 0.05 * Cm.mean() if epsilon is None else float(epsilon)
+    la, lb = -np.log(n), -np.log(m)
+    f, g = np.zeros(n), np.zeros(m)
+    it, err, conv = 0, np.inf, False
+    while it < max_iterations and not conv:
+        for k in range(inner_iterations):
+            if it >= max_iterations:
+                break
+            g = -eps * (logsumexp((f[:, None] - Cm) / eps, axis=0) + la)
+            f_new = -eps * (logsumexp((g[None, :] - Cm) / eps, axis=1) + lb)
+            if k == inner_iterations - 1 or it == max_iterations - 1:
+                err = float(np.sum(np.abs(np.exp((f - f_new) / eps) - 1.0)) / n)
+            f = f_new
+            it += 1
+        conv = err < threshold
+    P_sum = np.exp((f[:, None] + g[None, :] - Cm) / eps).sum() / (n * m)
+    val = f.mean() + g.mean() + eps * (1.0 - P_sum)
+    if return_info:
+        return float(val), dict(iterations=it, error=err, converged=conv, epsilon=eps, f=f, g=g)
+    return float(val)

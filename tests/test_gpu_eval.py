@@ -95,7 +95,7 @@ def test_argument_errors():
     with pytest.raises(ValueError):
         ev.cost_matrix(x, y, ord=0.5)
     with pytest.raises(NotImplementedError):
-        ev.wasserstein_sinkhorn(x, y)
+        ev.wasserstein_sinkhorn(x, y, cost_fn=object())
 
 
 # ---- optimal assignment on the GPU (csrc/assign.cu) -----------------------------------------------------------------
@@ -179,4 +179,43 @@ def test_assignment_at_the_reference_size():
     cur = cm[i, cols[i]].double() + cm[k, cols[k]].double()
     swp = cm[i, cols[k]].double() + cm[k, cols[i]].double()
     assert float((cur - swp).max()) <= 2.0 * float(cm.max()) * 2.0 ** -23
+    assert dt < 3.0, dt
+
+
+# ---- Sinkhorn (csrc/sinkhorn.cu) --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m,d,eps", [(300, 300, 10, None), (257, 400, 26, None), (500, 500, 4, 1e-2), (64, 33, 2, 0.5)])
+def test_sinkhorn_matches_the_float64_restatement(n, m, d, eps):
+    """wasserstein_sinkhorn (evaluation.py:69-97): same iteration count, same stopping decision and the same `ent_reg_cost` as the
+    NumPy float64 restatement of the algorithm (OTT's defaults as recalled).  A converged value is the unique optimum of the
+    entropy-regularised problem: between the optimal-assignment cost and the mean cost, and above <P, C> by eps KL."""
+    x, y = _samples(n, m, d, seed=n + m)
+    got, info = ev.wasserstein_sinkhorn(x, y, epsilon=eps, return_info=True)
+    want, winfo = oe.wasserstein_sinkhorn(x, y, epsilon=eps, return_info=True)
+    assert info["converged"] == winfo["converged"] and abs(info["iterations"] - winfo["iterations"]) <= 10
+    assert abs(info["epsilon"] - winfo["epsilon"]) < 1e-6 * winfo["epsilon"]
+    assert abs(got - want) < 2e-4 * max(1.0, abs(want)), (got, want, info, {k: winfo[k] for k in ("iterations", "error")})
+    cm = oe.distance_matrix(x, y, 2.0)
+    assert got < cm.mean() + 1e-6
+    if n == m:
+        assert got > oe.wasserstein_dist11_p(x, y, 2.0) - 1e-4     # eps KL >= 0 and <P, C> >= the unregularised optimum
+
+
+def test_sinkhorn_unbiased_and_reference_size():
+    x, y = _samples(400, 400, 10, seed=4)
+    a = ev.wasserstein_sinkhorn_unbiased(x, y)
+    b = oe.wasserstein_sinkhorn(x, y) - 0.5 * (oe.wasserstein_sinkhorn(x, x) + oe.wasserstein_sinkhorn(y, y))
+    assert abs(a - b) < 5e-4, (a, b)
+    assert abs(ev.wasserstein_sinkhorn_unbiased(x, x)) < 1e-6
+    # 10^4 x 10^4 (the size of compare_wasserstein.py's runs): time and sanity
+    import time
+    x, y = _samples(10000, 10000, 26, seed=12, shift=0.05)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    v, info = ev.wasserstein_sinkhorn(x, y, return_info=True)
+    dt = time.perf_counter() - t0
+    print(f"sinkhorn 10^4 x 10^4: {dt:.3f} s, {info}")
+    w1 = ev.wasserstein_dist11_p(x, y)
+    mean_cost = float(ev.cost_matrix(x, y, 2.0).double().mean())
+    # <P, C> + eps KL(P | a x b): above the unregularised optimum, below the independent coupling's cost (KL = 0 there)
+    assert info["converged"] and w1 - 1e-3 < v < mean_cost + 1e-6, (v, w1, mean_cost)
     assert dt < 3.0, dt
