@@ -53,9 +53,9 @@ def mmd_heuristic(x, y):
 
 def distance_matrix(u, v, p=2.0):
     """scipy.spatial.distance_matrix(u, v, p) (evaluation.py:58)"""
-    from scipy.spatial import distance_matrix as dm
+    from scipy.spatial.distance import cdist  # (scipy.spatial.distance_matrix itself is deprecated since SciPy 1.18: same Minkowski-p matrix)
 
-    return dm(np.asarray(u, np.float64), np.asarray(v, np.float64), p=p)
+    return cdist(np.asarray(u, np.float64), np.asarray(v, np.float64), metric="minkowski", p=p)
 
 
 def wasserstein_dist11_p(u, v, ord=2.0):
