@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
       if (lane == 0) {
         const uint32_t idesc = make_idesc_bf16_f32(TC_M, TC_TILE_N);
         constexpr uint32_t a_kstride = (TC_M / 8) * 128, b_kstride = (TC_TILE_N / 8) * 128;
+        const uint64_t da0 = make_smem_desc(smem_u32(sA), a_kstride, 128), db0 = make_smem_desc(smem_u32(sX), b_kstride, 128);
+        const uint32_t da_lo0 = (uint32_t)da0, da_hi = (uint32_t)(da0 >> 32), db_lo0 = (uint32_t)db0, db_hi = (uint32_t)(db0 >> 32);
+        constexpr uint32_t kAChunk = (2 * a_kstride) >> 4, kBChunk = (2 * b_kstride) >> 4;  // one K = 16 chunk, in descriptor units
         for (int64_t st = 0; st < p.n_steps; ++st) {
           for (int tile = 0; tile < p.n_tiles; ++tile, ++x_it) {
             const int s = x_it & 1;
@@ -142,13 +145,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_kernel(const TcPara
               const int b = acc_it & 1;
               mbar_wait(&acc_empty[b], ((acc_it >> 1) & 1) ^ 1);
               tc_fence_after();
-              const uint32_t a_base = smem_u32(sA + g * TC_A_BYTES), b_base = smem_u32(sX + s * TC_TILE_BYTES);
+              // hoisted base descriptors + chunk offsets in the low word: tcgen05.mma issue blocks the issuing thread, so its
+              // own instruction stream is tensor-pipe idle time (scripts/probes/umma_bench.cu: 128 vs 232 cycles per MMA)
+              const uint32_t a_lo = da_lo0 + (uint32_t)g * (TC_A_BYTES >> 4), b_lo = db_lo0 + (uint32_t)s * (TC_TILE_BYTES >> 4);
+              const uint32_t d = tmem_base + (uint32_t)(b * TC_TILE_N);
+              umma_bf16_lean<false>(d, a_lo, da_hi, b_lo, db_hi, idesc);
 #pragma unroll
-              for (int ks = 0; ks < TC_KP / 16; ++ks) {
-                const uint64_t da = make_smem_desc(a_base + 2 * ks * a_kstride, a_kstride, 128);
-                const uint64_t db = make_smem_desc(b_base + 2 * ks * b_kstride, b_kstride, 128);
-                umma_bf16(tmem_base + (uint32_t)(b * TC_TILE_N), da, db, idesc, ks > 0);
-              }
+              for (int ks = 1; ks < TC_KP / 16; ++ks)
+                umma_bf16_lean<true>(d, a_lo + ks * kAChunk, da_hi, b_lo + ks * kBChunk, db_hi, idesc);
               umma_commit(&acc_full[b]);
             }
             umma_commit(&x_empty[s]);
