@@ -198,13 +198,17 @@ __device__ __forceinline__ float tc_column_pass(float* __restrict__ col, const f
   return x.ss;
 }
 
-// Operand layout of THIS kernel: K = 64 for both operands, A' = [D_hi (25 + 7 zeros) | D_lo (25 + 7 zeros)],
-// B' = [X_hi | X_lo] likewise, and the three significant cross terms come from six K = 16 MMAs whose descriptors pick
-// the 16-column chunks (A, B) = (0,0) (1,1) | (2,0) (3,1) | (0,2) (1,3)  =  D_hi X_hi + D_lo X_hi + D_hi X_lo.
-// Compared with the K = 80 concatenation of diamonds_tc.cu this is one more MMA per accumulator (768 instead of 640
-// tensor cycles) but 20 % fewer bytes per design-matrix tile -- and this kernel is bound by SM <-> L2 traffic
-// (each stream re-reads every tile for only two groups), not by the tensor pipe.
+// Operand layout: the K = 80 concatenation of diamonds_tc.cu -- A' = [D_hi | D_lo | D_hi | 0] (25 + 25 + 25 + 5 columns),
+// B' = [X_hi | X_hi | X_lo | 0], five K = 16 MMAs per accumulator; the design-matrix tiles are the ones the shared-state
+// kernel uses.  Round 1 used K = 64 operands ([D_hi (25 + 7 zeros) | D_lo (25 + 7 zeros)] x [X_hi | X_lo], six MMAs whose
+// descriptors pick the chunk pairs; -DAMCMC_TCA_K64): 20 % fewer bytes per tile, which mattered when the kernel was thought to
+// be short of SM <-> L2 bandwidth.  It is not (profiles/r02_diamonds_tc_adaptive.md): it runs at the board's power limit, where
+// one MMA less per accumulator is worth more -- 33.2 vs 34.4 ms per 500 steps at 65,536 chains.
+#ifndef AMCMC_TCA_K64
+constexpr int TCA_K = 80;
+#else
 constexpr int TCA_K = 64;
+#endif
 constexpr int TCA_TILE_BYTES = TC_TILE_N * TCA_K * 2;  // 32768
 constexpr int TCA_A_BYTES = TC_M * TCA_K * 2;          // 16384
 constexpr int TCA_STAGES = 2;                          // design-matrix tiles in flight (a third stage was measured: no gain)
@@ -247,8 +251,13 @@ __device__ __forceinline__ void tc_emit_proposal(const float (&xp)[TC_D], const 
     hi[k] = h;
     lo[k] = f2bf(dlt - bf2f(h));
   }
+#ifndef AMCMC_TCA_K64
+  // K layout: [hi(25) | lo(25) | hi(25) | 0(5)]
+  auto elem = [&](int k) -> uint32_t { return k < TC_KC ? hi[k] : (k < 2 * TC_KC ? lo[k - TC_KC] : (k < 3 * TC_KC ? hi[k - 2 * TC_KC] : 0u)); };
+#else
   // K layout: [hi(25) | 0(7) | lo(25) | 0(7)]
   auto elem = [&](int k) -> uint32_t { return k < TC_KC ? hi[k] : (k < 32 ? 0u : (k < 32 + TC_KC ? lo[k - 32] : 0u)); };
+#endif
   unsigned char* arow = sA + g * TCA_A_BYTES + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
   for (int kc = 0; kc < TCA_K / 8; ++kc) {
@@ -427,6 +436,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
                 const uint32_t b_lo = db_lo0 + (uint32_t)s * (TCA_TILE_BYTES >> 4) + (uint32_t)h * (((TCA_ACC_N / 8) * 128) >> 4);
                 const uint32_t d = tmem_base + (uint32_t)(b * TCA_ACC_N);
                 // A chunks 0 1 | 2 3 | 0 1 (D_hi | D_lo | D_hi)  x  B chunks 0 1 | 0 1 | 2 3 (X_hi | X_hi | X_lo)
+#ifndef AMCMC_TCA_K64
+                umma_bf16_lean<false>(d, a_lo, da_hi, b_lo, db_hi, idesc);
+#pragma unroll
+                for (int ks = 1; ks < TCA_K / 16; ++ks)
+                  umma_bf16_lean<true>(d, a_lo + ks * kAChunk, da_hi, b_lo + ks * kBChunk, db_hi, idesc);
+#else
                 umma_bf16_lean<false>(d, a_lo, da_hi, b_lo, db_hi, idesc);
                 umma_bf16_lean<true>(d, a_lo + kAChunk, da_hi, b_lo + kBChunk, db_hi, idesc);
                 if (!(ap.dbg & 2u)) {
@@ -435,6 +450,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) diamonds_tc_adapt_kernel(const 
                   umma_bf16_lean<true>(d, a_lo, da_hi, b_lo + 2 * kBChunk, db_hi, idesc);
                   umma_bf16_lean<true>(d, a_lo + kAChunk, da_hi, b_lo + 3 * kBChunk, db_hi, idesc);
                 }
+#endif
                 umma_commit(&acc_full[strm * TCA_NBUF + b]);
                 ++k;
               }
@@ -754,7 +770,11 @@ int run_diamonds_tc_adapt(const amcmc_model* m, const amcmc_state* st, const amc
     ex->cref_cap = C;
   }
   ap.cref = ex->cref;
+#ifndef AMCMC_TCA_K64
+  ap.Xcanon64 = ex->Xcanon;   // the K = 80 tiles of the shared-state kernel
+#else
   ap.Xcanon64 = ex->Xcanon64;
+#endif
   ap.crss = ex->crss;
   tc_chol_to_ldl_kernel<<<ap.p.n_groups, TC_M, 0, s>>>((const float*)st->scale, ap.ldl, C);
   int dev = 0, sms = 148;
