@@ -14,6 +14,8 @@
 #include <climits>
 #include <cstring>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "internal.h"
 
@@ -130,13 +132,56 @@ __global__ void auction_assign_kernel(int n, int* __restrict__ col_of, int* __re
 // instead of ~20 us per round.  The queue holds at most kTailQueue rows (the number of unassigned rows never grows).
 constexpr int kTailThreads = 1024;
 constexpr int kTailQueue = 256;
+constexpr int kTailSmemCols = 18000;  // up to this many columns, prices and owners live in shared memory during the tail (216 KB)
 
+// The tail works on reduced costs r_j = c_ij (n + 1) + price_j >= 0 (the value of column j is -r_j) as unsigned 64-bit
+// integers: one IMAD.WIDE.U32 per element, and the two smallest are kept with selects (the lanes of a warp would diverge
+// on almost every element with branches).  A thread visits its columns in increasing order, so a tie keeps the earlier one.
+struct Low2 {
+  unsigned long long best, second;
+  int arg;
+};
+constexpr unsigned long long kNoCost = ~0ull;
+__device__ __forceinline__ void low2_push(Low2& t, unsigned int c, unsigned int np1, unsigned long long price, int j) {
+  const unsigned long long v = (unsigned long long)c * np1 + price;
+  const bool lt = v < t.best;
+  const unsigned long long s2 = v < t.second ? v : t.second;
+  t.second = lt ? t.best : s2;
+  t.best = lt ? v : t.best;
+  t.arg = lt ? j : t.arg;
+}
+// 64-bit unsigned minimum over a warp with two 32-bit redux.sync instead of five shuffle levels of 64-bit values
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned h = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned l = __reduce_min_sync(0xffffffffu, hi == h ? lo : 0xffffffffu);
+  return ((unsigned long long)h << 32) | l;
+}
+// the two smallest over the warp's 32 partial results; every lane returns the same (ties: lowest column index)
+__device__ __forceinline__ Low2 warp_low2(const Low2& t) {
+  Low2 r;
+  r.best = warp_min_u64(t.best);
+  r.arg = __reduce_min_sync(0xffffffffu, t.best == r.best ? t.arg : INT_MAX);
+  const bool win = (t.best == r.best) && (t.arg == r.arg);  // exactly one lane: column indices are distinct (or all INT_MAX)
+  r.second = warp_min_u64(win ? t.second : t.best);
+  return r;
+}
+
+// SMEM_STATE: the CTA owns prices and column owners while it runs (nobody else bids), so they are staged in shared memory
+// and written back at the end; a bid then only streams the row's n int32 costs, with all of a thread's 16-byte loads issued
+// before the first comparison.  Measured per bid at n = 10^4 (clock64 build, -DAMCMC_ASSIGN_TIMING): 10.9k cycles with the
+// warp results merged by shuffles and the 32 warps merged serially by thread 0 (6.0k scan + reduce, 4.7k merge + update);
+// redux.sync merges at both levels bring it to the figure in profiles/r02_eval.md.
+template <bool SMEM_STATE>
 __global__ void __launch_bounds__(kTailThreads)
-auction_tail_kernel(const int32_t* __restrict__ ci, int n, volatile long long* price, volatile int* col_of, volatile int* row_of,
+auction_tail_kernel(const int32_t* __restrict__ ci, int n, long long* price_g, volatile int* col_of, int* row_of_g,
                     long long eps, int* __restrict__ n_unassigned, long long max_bids, unsigned long long* __restrict__ bids_done) {
+  extern __shared__ long long s_dyn[];
+  long long* s_price = s_dyn;
+  int* s_owner = reinterpret_cast<int*>(s_dyn + n);
   __shared__ int queue[kTailQueue];
   __shared__ int q_count;
-  __shared__ Top2 sh[kTailThreads / 32];
+  __shared__ Low2 sh[kTailThreads / 32];
   if (threadIdx.x == 0) q_count = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += kTailThreads)
@@ -146,37 +191,89 @@ auction_tail_kernel(const int32_t* __restrict__ ci, int n, volatile long long* p
     }
   __syncthreads();
   if (q_count > kTailQueue) return;  // too many for the tail: the caller goes on with Jacobi rounds
-  const long long np1 = (long long)n + 1;
+  if (SMEM_STATE)
+    for (int j = threadIdx.x; j < n; j += kTailThreads) { s_price[j] = price_g[j]; s_owner[j] = row_of_g[j]; }
+  long long* price = SMEM_STATE ? s_price : price_g;
+  int* row_of = SMEM_STATE ? s_owner : row_of_g;
+  __syncthreads();
+  const unsigned int np1 = (unsigned int)n + 1u;
+  const bool vec = (n % 4 == 0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   long long done = 0;
-  while (q_count > 0 && done < max_bids) {
-    const int i = queue[q_count - 1];
+#ifdef AMCMC_ASSIGN_TIMING
+  long long tk[4] = {0, 0, 0, 0};
+#define AT(k) { const long long c_ = clock64(); tk[k] += c_ - tl; tl = c_; }
+#else
+#define AT(k)
+#endif
+  int nq = q_count;
+  while (nq > 0 && done < max_bids) {
+#ifdef AMCMC_ASSIGN_TIMING
+    long long tl = clock64();
+#endif
+    const int i = queue[nq - 1];
+#ifdef AMCMC_ASSIGN_FIXROW
+    const int32_t* row = ci + (int64_t)(i & 63) * n;
+#else
     const int32_t* row = ci + (int64_t)i * n;
-    Top2 t{kNoBid, kNoBid, INT_MAX};
-    for (int j = threadIdx.x; j < n; j += kTailThreads) top2_push(t, -(long long)__ldg(row + j) * np1 - price[j], j);
-    for (int o = 16; o; o >>= 1) {
-      Top2 u;
-      u.best = __shfl_xor_sync(0xffffffffu, t.best, o);
-      u.second = __shfl_xor_sync(0xffffffffu, t.second, o);
-      u.arg = __shfl_xor_sync(0xffffffffu, t.arg, o);
-      top2_merge(t, u);
+#endif
+    Low2 t{kNoCost, kNoCost, INT_MAX};
+    if (vec) {
+      const int4* row4 = reinterpret_cast<const int4*>(row);
+      const int n4 = n >> 2;
+      for (int q0 = threadIdx.x; q0 < n4; q0 += 4 * kTailThreads) {  // four independent 16-byte loads in flight per thread
+        int4 c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * kTailThreads;
+          c[u] = q < n4 ? __ldcs(row4 + q) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int q = q0 + u * kTailThreads;
+          if (q < n4) {
+            const int j = 4 * q;
+            low2_push(t, (unsigned int)c[u].x, np1, (unsigned long long)price[j], j);
+            low2_push(t, (unsigned int)c[u].y, np1, (unsigned long long)price[j + 1], j + 1);
+            low2_push(t, (unsigned int)c[u].z, np1, (unsigned long long)price[j + 2], j + 2);
+            low2_push(t, (unsigned int)c[u].w, np1, (unsigned long long)price[j + 3], j + 3);
+          }
+        }
+      }
+    } else {
+      for (int j = threadIdx.x; j < n; j += kTailThreads) low2_push(t, (unsigned int)__ldg(row + j), np1, (unsigned long long)price[j], j);
     }
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    t = warp_low2(t);
+    AT(0)
+    if (lane == 0) sh[warp] = t;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < kTailThreads / 32; ++w) top2_merge(t, sh[w]);
-      const long long gap = t.second == kNoBid ? 0 : t.best - t.second;
-      const int j = t.arg;
-      const int prev = row_of[j];
-      price[j] = price[j] + gap + eps;
-      row_of[j] = i;
-      col_of[i] = j;
-      if (prev >= 0) { col_of[prev] = -1; queue[q_count - 1] = prev; }  // the evicted owner takes the slot of the popped row
-      else { q_count = q_count - 1; atomicSub(n_unassigned, 1); }
-      __threadfence_block();
+    AT(1)
+    if (warp == 0) {  // warp 0 merges the 32 warp results and applies the bid
+      t = warp_low2(sh[lane]);
+      if (lane == 0) {
+        const int j = t.arg;
+        const int prev = row_of[j];
+        const long long gap = t.second == kNoCost ? 0 : (long long)(t.second - t.best);  // n == 1: no competitor
+        price[j] = price[j] + gap + eps;
+        row_of[j] = i;
+        col_of[i] = j;
+        if (prev >= 0) { col_of[prev] = -1; queue[nq - 1] = prev; }  // the evicted owner takes the slot of the popped row
+        else { q_count = nq - 1; atomicSub(n_unassigned, 1); }
+      }
     }
+    AT(2)
     ++done;
     __syncthreads();
+    nq = q_count;
+    AT(3)
   }
+#ifdef AMCMC_ASSIGN_TIMING
+  if (threadIdx.x == 0 && done > 0)
+    printf("[tail] bids %lld: own scan+reduce %lld, wait others %lld, merge+update %lld, sync %lld cycles per bid\n", done,
+           tk[0] / done, tk[1] / done, tk[2] / done, tk[3] / done);
+#endif
+  if (SMEM_STATE)
+    for (int j = threadIdx.x; j < n; j += kTailThreads) { price_g[j] = s_price[j]; row_of_g[j] = s_owner[j]; }
   if (threadIdx.x == 0) atomicAdd(bids_done, (unsigned long long)done);
 }
 
@@ -240,17 +337,30 @@ extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* co
   assign_max_kernel<<<gs, 256, 0, s>>>(cost, total, scal);
   assign_quantise_kernel<<<gs, 256, 0, s>>>(cost, total, scal, ci);
   const unsigned nb = (unsigned)((n + 255) / 256);
+  if (n <= kTailSmemCols && (size_t)n * 12 > 48 * 1024 &&
+      (rc = check_cuda(cudaFuncSetAttribute(auction_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemCols * 12),
+                       "cudaFuncSetAttribute(auction_tail_kernel)"))) { cudaFree(buf); return rc; }
   // epsilon-scaling on costs multiplied by (n + 1): start at ~1/8 of the largest scaled cost, divide by 6 down to 1
   long long eps = ((long long)16777215 * (n + 1)) / 8;
   if (eps < 1) eps = 1;
   long rounds = 0, host_iters = 0;
+  const bool dbg = getenv("AMCMC_ASSIGN_DEBUG") != nullptr;  // per-phase breakdown on stderr (scripts/probes/assign_perf.py)
+  double ms_tail = 0, ms_jac = 0;
+  long n_tail = 0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
   unsigned long long* tail_bids = (unsigned long long*)(scal + 8);
   for (;;) {
     auction_reset_kernel<<<nb, 256, 0, s>>>(n, col_of, row_of, maxbid, winner, n_un);
     int un = n;
     while (un > 0) {
-      if (un <= kTailQueue / 2) {  // few rows left: finish the phase in one CTA (Gauss-Seidel order)
-        auction_tail_kernel<<<1, kTailThreads, 0, s>>>(ci, n, price, col_of, row_of, eps, n_un, (long long)1 << 22, tail_bids);
+      const bool tail = un <= kTailQueue / 2;
+      if (dbg) cudaEventRecord(e0, s);
+      if (tail) {  // few rows left: finish the phase in one CTA (Gauss-Seidel order)
+        if (n <= kTailSmemCols)
+          auction_tail_kernel<true><<<1, kTailThreads, (size_t)n * 12, s>>>(ci, n, price, col_of, row_of, eps, n_un, (long long)1 << 22, tail_bids);
+        else
+          auction_tail_kernel<false><<<1, kTailThreads, 0, s>>>(ci, n, price, col_of, row_of, eps, n_un, (long long)1 << 22, tail_bids);
       } else {
         for (int r = 0; r < 4; ++r) {
           auction_bid_kernel<<<n, kBidThreads, 0, s>>>(ci, n, price, col_of, eps, maxbid, bid_val, bid_col);
@@ -260,8 +370,15 @@ extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* co
         rounds += 4;
       }
       if ((rc = check_cuda(cudaMemcpyAsync(&un, n_un, 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync"))) { cudaFree(buf); return rc; }
+      if (dbg) cudaEventRecord(e1, s);
       if ((rc = check_cuda(cudaStreamSynchronize(s), "auction round"))) { cudaFree(buf); return rc; }
+      if (dbg) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); if (tail) { ms_tail += ms; ++n_tail; } else ms_jac += ms; }
       if (++host_iters > 2000000) { cudaFree(buf); set_error("amcmc_eval_assignment: auction did not terminate"); return AMCMC_ERR_CUDA; }
+    }
+    if (dbg) {
+      unsigned long long tb = 0;
+      cudaMemcpy(&tb, tail_bids, 8, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[assign] eps %lld: jacobi rounds %ld (%.2f ms)  tail launches %ld bids %llu (%.2f ms)\n", eps, rounds, ms_jac, n_tail, tb, ms_tail);
     }
     if (eps == 1) break;
     eps /= 6;
@@ -278,6 +395,7 @@ extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* co
     cudaMemcpy(&tb, tail_bids, 8, cudaMemcpyDeviceToHost);
     out_host[0] = tf; out_host[1] = (double)ti; out_host[2] = (double)rounds + (double)tb;  // Jacobi rounds + Gauss-Seidel bids
   }
+  if (dbg) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
   rc = check_cuda(cudaGetLastError(), "amcmc_eval_assignment");
   cudaFree(buf);
   return rc;
