@@ -203,6 +203,12 @@ int amcmc_selftest_umma(const void* a_bf16, const void* b_bf16, int K, void* scr
  * (:201-222) without materialising the n x m matrix. */
 int amcmc_eval_kernel_sum(const float* x, int64_t n, const float* y, int64_t m, int d, double gamma, int skip_diagonal,
                           double* out_host, void* stream);
+/* The three sums of mmd2_unbiased / mmd_heuristic (evaluation.py:246-263, :279-294) in one launch on the tensor cores:
+ * out_host[0] = sum_{i != j} k(x_i, x_j), [1] = sum_{i != j} k(y_i, y_j), [2] = sum_ij k(x_i, y_j), k(a, b) = exp(-gamma |a - b|^2)
+ * (add n resp. m for the diagonals of the biased estimate: k(a, a) = 1).  The cross terms are a bf16-split tcgen05 GEMM
+ * (hi.hi + lo.hi + hi.lo, fp32 accumulation), exp in the epilogue.  d <= 32, else AMCMC_ERR_UNSUPPORTED (use
+ * amcmc_eval_kernel_sum, any d, CUDA cores).  Synchronises `stream`. */
+int amcmc_eval_mmd_sums(const float* x, int64_t n, const float* y, int64_t m, int d, double gamma, double* out_host, void* stream);
 /* Median of all m*m squared pairwise distances of y (diagonal zeros and both orders included): the bandwidth
  * heuristic gamma = 4 / median (evaluation.py:283).  Exact radix select on the float32 keys, no m*m buffer. */
 int amcmc_eval_sqdist_median(const float* y, int64_t m, int d, double* out_host, void* stream);

@@ -13,8 +13,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "adaptive_mcmc_b200", "csrc")
 OUT = os.path.join(ROOT, "profiles", "sass")
-OBJECTS = ["diamonds_tc_adapt.o", "diamonds_tc.o", "tc_selftest.o"]
-PAT = re.compile(r"\b(UTCHMMA|UTCQMMA|UTCBAR|UTCATOMSWS|UTCALLOC|LDTM|STTM|UBLKCP|UTMALDG|UTMASTG|SYNCS|FFMA2|SETMAXREG|USETMAXREG|ELECT)\b[.\w]*")
+OBJECTS = ["diamonds_tc_adapt.o", "diamonds_tc.o", "mmd_tc.o", "tc_selftest.o"]
+PAT = re.compile(r"\b(UTCHMMA|UTCQMMA|UTCBAR|UTCATOMSWS|UTCALLOC|LDTM|STTM|UBLKCP|UTMALDG|UTMASTG|SYNCS|FFMA2|MUFU\.EX2|SETMAXREG|USETMAXREG|ELECT)\b[.\w]*")
 
 
 def main():

@@ -219,3 +219,73 @@ def test_sinkhorn_unbiased_and_reference_size():
     # <P, C> + eps KL(P | a x b): above the unregularised optimum, below the independent coupling's cost (KL = 0 there)
     assert info["converged"] and w1 - 1e-3 < v < mean_cost + 1e-6, (v, w1, mean_cost)
     assert dt < 3.0, dt
+
+
+# ---- the three kernel sums of the MMD estimators on the tensor cores (csrc/mmd_tc.cu) ---------------------------------
+
+def _sums64(x, y, gamma):
+    """float64 NumPy: (sum_{i != j} k(x_i, x_j), sum_{i != j} k(y_i, y_j), sum_ij k(x_i, y_j))"""
+    def k(a, b):
+        a, b = a.astype(np.float64), b.astype(np.float64)
+        d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2 * a @ b.T
+        return np.exp(-gamma * np.maximum(d2, 0))
+    return k(x, x).sum() - len(x), k(y, y).sum() - len(y), k(x, y).sum()
+
+
+@pytest.mark.parametrize("n,m,d", [(300, 257, 10), (129, 400, 26), (64, 64, 4), (50, 33, 1), (1000, 1500, 32), (128, 256, 16), (1, 1, 3),
+                                   (385, 2, 11)])
+def test_tensor_core_kernel_sums_match_float64(n, m, d):
+    """ragged tile counts, d from 1 to the limit 32, one-point samples.  The two-term bf16 split carries a cross product to
+    ~2^-17 |a||b| (lo.lo dropped, lo rounded), i.e. gamma |a||b| 1e-5 on one kernel value, zero-mean over the pairs: 1e-5 on the
+    sums of these few-hundred-point samples (measured up to 5.3e-6), 2e-6 at the reference size (next tests); the CUDA-core
+    passes, fp32 differences, stay at 2e-6 here too -- `impl="auto"` takes them below 1,024 points."""
+    x, y = _samples(n, m, d, seed=n + d)
+    med = oe.median_sqdist(y) if m > 1 else 1.0
+    for gamma in (4.0 / med, 1.0, 0.0):
+        got = ev.mmd_kernel_sums(x, y, gamma, impl="tc")
+        want = _sums64(x, y, gamma)
+        cuda = ev.mmd_kernel_sums(x, y, gamma, impl="cuda")
+        for g, w, c in zip(got, want, cuda):
+            assert abs(g - w) <= 1e-5 * abs(w) + 1e-6, (gamma, got, want)
+            assert abs(c - w) <= 2e-6 * abs(w) + 1e-6, (gamma, cuda, want)
+
+
+def test_tensor_core_kernel_sums_far_from_the_origin():
+    """samples with a large common offset (eight_schools' mu, tau ~ 10): centring on the mean of y keeps the split exact enough"""
+    x, y = _samples(700, 900, 10, seed=5)
+    x, y = x + 40.0, y + 40.0
+    med = oe.median_sqdist(y)
+    got, want = ev.mmd_kernel_sums(x, y, 4.0 / med, impl="tc"), _sums64(x, y, 4.0 / med)
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 3e-6 * abs(w), (got, want)
+
+
+def test_mmd_estimators_agree_between_the_two_paths_and_with_the_oracle():
+    x, y = _samples(800, 700, 26, seed=3, shift=0.1)
+    assert abs(ev.mmd_heuristic(x, y, impl="tc") - oe.mmd_heuristic(x, y)) < 2e-5
+    assert abs(ev.mmd_heuristic(x, y, impl="tc") - ev.mmd_heuristic(x, y, impl="cuda")) < 2e-5
+    assert abs(ev.mmd2_unbiased(x, y, gamma=0.7, impl="tc") - oe.mmd2_unbiased(x, y, gamma=0.7)) < 2e-6
+    with pytest.raises(ValueError):
+        ev.mmd_kernel_sums(np.zeros((4, 40), np.float32), np.zeros((4, 40), np.float32), 1.0, impl="tc")
+    s = ev.mmd_kernel_sums(*_samples(40, 30, 40, seed=1), 0.5)   # d > 32: "auto" takes the CUDA-core passes
+    w = _sums64(*_samples(40, 30, 40, seed=1), 0.5)
+    assert all(abs(a - b) <= 2e-6 * abs(b) + 1e-6 for a, b in zip(s, w))
+
+
+def test_tensor_core_kernel_sums_at_the_reference_size():
+    """n = m = 10^4, d = 26 and d = 10: against a float64 torch evaluation, and the estimator identities"""
+    for d in (26, 10):
+        x, y = _samples(10000, 10000, d, seed=d, shift=0.05)
+        xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+        g = 4.0 / ev.sqdist_median(yt)
+        sxx, syy, sxy = ev.mmd_kernel_sums(xt, yt, g, impl="tc")
+        kxy = torch.exp(-g * torch.cdist(xt.double(), yt.double()) ** 2).sum().item()
+        kxx = torch.exp(-g * torch.cdist(xt.double(), xt.double()) ** 2).sum().item() - 10000
+        kyy = torch.exp(-g * torch.cdist(yt.double(), yt.double()) ** 2).sum().item() - 10000
+        for got, want in ((sxx, kxx), (syy, kyy), (sxy, kxy)):
+            assert abs(got - want) < 2e-6 * want, (got, want)
+        # swapping the samples swaps the same-sample sums and keeps the cross sum (centre moves from mean(y) to mean(x))
+        txx, tyy, txy = ev.mmd_kernel_sums(yt, xt, g, impl="tc")
+        assert abs(txx - syy) < 2e-6 * syy and abs(tyy - sxx) < 2e-6 * sxx and abs(txy - sxy) < 2e-6 * sxy
+        same = ev.mmd_heuristic(xt, xt)
+        assert same != same or same < 2e-3
