@@ -205,10 +205,15 @@ extern "C" int amcmc_eval_sqdist_median(const float* y, int64_t m, int d, double
   // jnp.median of an even count = mean of the two middle order statistics
   const unsigned long long ranks[2] = {(total - 1) / 2, total / 2};
   float vals[2] = {0.f, 0.f};
+  // The upper middle rank is the next order statistic: it is found in the histograms of the lower one as long as it stays in the
+  // same bin (or, in the last pass, in the next non-empty bin of the same prefix); only when the two ranks part in an earlier
+  // pass (their keys differ above bit 10) is the select run again for it.
+  bool second_known = ranks[1] == ranks[0];
   for (int r = 0; r < 2 && !rc; ++r) {
-    if (r == 1 && ranks[1] == ranks[0]) { vals[1] = vals[0]; break; }
+    if (r == 1 && second_known) { if (ranks[1] == ranks[0]) vals[1] = vals[0]; break; }
     unsigned long long k = ranks[r];
     uint32_t prefix = 0;
+    bool together = (r == 0) && !second_known;  // rank k + 1 still shares the prefix
     const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
     for (int pass = 0; pass < 3 && !rc; ++pass) {
       const int nb = 1 << bits[pass];
@@ -224,10 +229,23 @@ extern "C" int amcmc_eval_sqdist_median(const float* y, int64_t m, int d, double
         cum += hh[b];
       }
       if (b == nb) { set_error("evaluation: median select ran past the histogram (NaN distances?)"); rc = AMCMC_ERR_ARG; break; }
+      if (together && k + 1 >= cum + hh[b]) {  // rank k + 1 is the first key of a later bin
+        together = false;
+        if (pass == 2) {                       // all 32 bits resolved: the next non-empty bin IS the value
+          int b2 = b + 1;
+          while (b2 < nb && hh[b2] == 0) ++b2;
+          if (b2 < nb) {
+            const uint32_t key = (prefix << bits[pass]) | (uint32_t)b2;
+            std::memcpy(&vals[1], &key, 4);
+            second_known = true;
+          }
+        }
+      }
       k -= cum;
       prefix = (prefix << bits[pass]) | (uint32_t)b;
     }
     std::memcpy(&vals[r], &prefix, 4);
+    if (r == 0 && together) { vals[1] = vals[0]; second_known = true; }
   }
   if (!rc) *out_host = (double)(vals[0] + (vals[1] - vals[0]) * 0.5f);
   return rc;

@@ -41,6 +41,23 @@ def test_median_even_and_odd_counts(m):
     assert abs(ev.sqdist_median(y) - oe.median_sqdist(y)) <= 4e-6 * oe.median_sqdist(y)
 
 
+@pytest.mark.parametrize("m", [2, 4, 6, 10, 50, 333, 2000, 4001])
+def test_median_is_the_exact_order_statistic_in_one_dimension(m):
+    """d = 1: the float32 squared distance is the rounded square of the rounded difference on both sides, so the select must
+    return the middle order statistics bit for bit (even m*m: both, found from one set of histogram passes -- same bin, next
+    bin of the last pass, or parted earlier and selected again)"""
+    rng = np.random.default_rng(m)
+    y = rng.normal(size=(m, 1)).astype(np.float32)
+    if m == 4:
+        y = np.array([[0.0], [1.0], [3.0], [7.0]], np.float32)   # middle ranks 4 and 9: they part in the first pass
+    d2 = ((y[:, None, 0] - y[None, :, 0]).astype(np.float32) ** 2).astype(np.float32).ravel()
+    srt = np.sort(d2)
+    lo, hi = srt[(d2.size - 1) // 2], srt[d2.size // 2]
+    want = (float(lo) + float(hi)) / 2
+    got = ev.sqdist_median(y)
+    assert abs(got - want) <= 1.2e-7 * abs(want), (got, want, lo, hi)
+
+
 @pytest.mark.parametrize("ord", [1.0, 2.0, 3.0])
 def test_cost_matrix_and_assignment(ord):
     x, y = _samples(150, 150, 10, seed=5)
