@@ -16,7 +16,7 @@ AMCMC_F32, AMCMC_F64 = 0, 1
 RNG_PHILOX, RNG_EXTERNAL = 0, 1
 KERNEL_ARWMH, KERNEL_RAM, KERNEL_ASSS = 0, 1, 2
 MODEL_STD_NORMAL, MODEL_EIGHT_SCHOOLS, MODEL_KIDIQ, MODEL_DIAMONDS, MODEL_GAUSSIAN, MODEL_CUSTOM = 0, 1, 2, 3, 4, 5
-IMPL_AUTO, IMPL_REGISTER, IMPL_BLOCK, IMPL_TENSOR = 0, 1, 2, 3
+IMPL_AUTO, IMPL_REGISTER, IMPL_BLOCK, IMPL_TENSOR, IMPL_REGISTER_BALANCED = 0, 1, 2, 3, 4
 
 
 class AmcmcState(C.Structure):

@@ -265,23 +265,20 @@ AMCMC_HD void arwmh_steps(ChainRegs<R, Model::D>& s, const Model& m, const RunVi
   }
 }
 
-// The whole per-chain launch body (host-compilable for tests/hostsim).  The launch is cut at the collection points
-// (numpyro.util.fori_collect as used at python/utils/kernel_utils.py:29-32: sample k = state after
-// collect_start + (k+1) thinning steps) so that the hot loop carries no collection bookkeeping, and its last step is
-// peeled: it alone computes as_change (arwmh.py:197).
+// Steps [t, t_end) of the launch for one chain whose state is in `s` (host-compilable for tests/hostsim).  The range is cut
+// at the collection points (numpyro.util.fori_collect as used at python/utils/kernel_utils.py:29-32: sample k = state after
+// collect_start + (k+1) thinning steps) so that the hot loop carries no collection bookkeeping, and the last step of the
+// LAUNCH is peeled: it alone computes as_change (arwmh.py:197).  Any split of [0, n_steps) into consecutive ranges gives
+// the same trajectory and the same samples.
 template <class Model, typename R, bool ADAPT, bool EXTERNAL>
-AMCMC_HD void arwmh_chain_run(const Model& m, const StateView<R>& st, const RunView<R>& a, int64_t c) {
+AMCMC_HD void arwmh_chain_range(ChainRegs<R, Model::D>& s, const Model& m, const RunView<R>& a, const Philox& rng, int64_t C,
+                                int64_t c, int64_t t, int64_t t_end) {
   constexpr int D = Model::D;
-  const int64_t C = st.C;
-  ChainRegs<R, D> s;
-  load_chain(s, st, c);
-  const Philox rng(a.seed, (uint64_t)(c + a.chain_offset));
   const int64_t T = a.n_steps;
-  int64_t next_collect = a.collect_start + a.thinning;  // number of completed steps at which the next sample is taken
-  int64_t sidx = 0;
-  int64_t t = 0;
-  while (t < T) {
-    const int64_t seg_end = next_collect < T ? next_collect : T;
+  int64_t sidx = t > a.collect_start ? (t - a.collect_start) / a.thinning : 0;   // samples taken before this range
+  int64_t next_collect = a.collect_start + (sidx + 1) * a.thinning;  // number of completed steps at which the next sample is taken
+  while (t < t_end) {
+    const int64_t seg_end = next_collect < t_end ? next_collect : t_end;
     const int64_t hot_end = seg_end < T ? seg_end : T - 1;
     arwmh_steps<Model, R, ADAPT, EXTERNAL>(s, m, a, rng, C, c, t, hot_end);
     t = hot_end;
@@ -305,6 +302,16 @@ AMCMC_HD void arwmh_chain_run(const Model& m, const StateView<R>& st, const RunV
       next_collect += a.thinning;
     }
   }
+}
+
+// The whole per-chain launch body.
+template <class Model, typename R, bool ADAPT, bool EXTERNAL>
+AMCMC_HD void arwmh_chain_run(const Model& m, const StateView<R>& st, const RunView<R>& a, int64_t c) {
+  constexpr int D = Model::D;
+  ChainRegs<R, D> s;
+  load_chain(s, st, c);
+  const Philox rng(a.seed, (uint64_t)(c + a.chain_offset));
+  arwmh_chain_range<Model, R, ADAPT, EXTERNAL>(s, m, a, rng, st.C, c, 0, a.n_steps);
   store_chain<R, D, ADAPT>(s, st, c);
 }
 
@@ -315,6 +322,125 @@ arwmh_small_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st.C) return;
   arwmh_chain_run<Model, R, ADAPT, EXTERNAL>(m, st, a, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Balanced variant: one 16-warp CTA per SM, warps take (chain group, segment of steps) items from a queue.
+//
+// A warp of arwmh_small_kernel owns its 32 chains for the whole launch, so the number of warps per scheduler is fixed by the
+// chain count: 65,536 chains on 148 SMs are 13.8 warps per SM = 4 + 4 + 3 + 3 per scheduler, and the launch lasts as long as
+// the schedulers with 4 (measured, chain-steps/s at 1 / 2 / 3 / 3.5 / 4 warps per scheduler: 2.60 / 3.63 / 3.74 / 3.33 / 3.80
+// x 10^10 -- a scheduler is saturated from 2 warps on, and 65,536 chains take exactly as long as 75,776).  Here every SM runs
+// 16 worker warps (4 per scheduler) over its ~14 groups of 32 chains: a worker pops a group, runs `seg` steps with the state
+// in registers, parks the registers (bit for bit, no LDL^T <-> Cholesky conversion) in the group's shared-memory slot and
+// pushes the group back.  All four schedulers stay saturated until the SM's work is done: 14/16 of the time.  The
+// trajectories do not depend on the schedule (counter RNG, raw register hand-off).
+// ---------------------------------------------------------------------------------------------
+constexpr int kBalWarps = 16;
+constexpr int kBalQueue = 32;  // ring capacity >= groups per CTA
+
+template <typename R, int D> struct ChainSlot {
+  static constexpr int NREG = 3 * D + ChainRegs<R, D>::NL + 4;
+  static AMCMC_HD void save(const ChainRegs<R, D>& s, R* slot, int lane) {
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) slot[(r++) * 32 + lane] = s.x[k];
+#pragma unroll
+    for (int k = 0; k < D; ++k) slot[(r++) * 32 + lane] = s.mu[k];
+#pragma unroll
+    for (int k = 0; k < D; ++k) slot[(r++) * 32 + lane] = s.Dg[k];
+#pragma unroll
+    for (int k = 0; k < ChainRegs<R, D>::NL; ++k) slot[(r++) * 32 + lane] = s.Lt[k];
+    slot[(r++) * 32 + lane] = s.U;
+    slot[(r++) * 32 + lane] = s.lam;
+    slot[(r++) * 32 + lane] = s.macc;
+    slot[(r++) * 32 + lane] = s.asc;
+  }
+  static AMCMC_HD void restore(ChainRegs<R, D>& s, const R* slot, int lane) {
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) s.x[k] = slot[(r++) * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < D; ++k) s.mu[k] = slot[(r++) * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < D; ++k) s.Dg[k] = slot[(r++) * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < ChainRegs<R, D>::NL; ++k) s.Lt[k] = slot[(r++) * 32 + lane];
+    s.U = slot[(r++) * 32 + lane];
+    s.lam = slot[(r++) * 32 + lane];
+    s.macc = slot[(r++) * 32 + lane];
+    s.asc = slot[(r++) * 32 + lane];
+  }
+};
+
+template <class Model, typename R, bool ADAPT, bool EXTERNAL>
+__global__ void __launch_bounds__(32 * kBalWarps, 1)
+arwmh_small_balanced_kernel(const Model m, const StateView<R> st, const RunView<R> a, int64_t n_groups, int seg) {
+  constexpr int D = Model::D;
+  using Slot = ChainSlot<R, D>;
+  extern __shared__ __align__(16) unsigned char bal_smem[];
+  __shared__ int q_ring[kBalQueue];
+  __shared__ int q_head, q_tail, q_left;
+  __shared__ int64_t t_done[kBalQueue];
+  R* slots = reinterpret_cast<R*>(bal_smem);
+  // this CTA's groups: a contiguous range, the remainder spread over the first CTAs
+  const int64_t base = n_groups / gridDim.x, rem = n_groups % gridDim.x;
+  const int64_t g0 = (int64_t)blockIdx.x * base + ((int64_t)blockIdx.x < rem ? blockIdx.x : rem);
+  const int ng = (int)(base + ((int64_t)blockIdx.x < rem ? 1 : 0));
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kBalQueue; ++k) { q_ring[k] = k < ng ? k : -1; t_done[k] = 0; }
+    q_head = 0;
+    q_tail = ng;
+    q_left = ng;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t C = st.C, T = a.n_steps;
+  for (;;) {
+    int item = -1;
+    if (lane == 0) {
+      const long long w0 = clock64();
+      for (;;) {
+        if (*(volatile int*)&q_left == 0) break;
+        const int h = *(volatile int*)&q_head;
+        if (h < *(volatile int*)&q_tail) {
+          if (atomicCAS(&q_head, h, h + 1) == h) {
+            do { item = atomicExch(&q_ring[h % kBalQueue], -1); } while (item < 0);  // the pusher publishes right after reserving
+            break;
+          }
+        } else {
+          __nanosleep(200);
+          if (clock64() - w0 > 200000000000LL) __trap();  // ~100 s: a scheduling bug must end as an error, not as a hung GPU
+        }
+      }
+    }
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item < 0) break;
+    const int64_t c = (g0 + item) * 32 + lane;
+    const int64_t t0 = t_done[item];
+    const int64_t t1 = t0 + seg < T ? t0 + seg : T;
+    R* slot = slots + (size_t)item * (Slot::NREG * 32);
+    if (c < C) {
+      ChainRegs<R, D> s;
+      if (t0 == 0) load_chain(s, st, c);
+      else Slot::restore(s, slot, lane);
+      const Philox rng(a.seed, (uint64_t)(c + a.chain_offset));
+      arwmh_chain_range<Model, R, ADAPT, EXTERNAL>(s, m, a, rng, C, c, t0, t1);
+      if (t1 == T) store_chain<R, D, ADAPT>(s, st, c);
+      else Slot::save(s, slot, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (t1 == T) {
+        atomicSub(&q_left, 1);
+      } else {
+        t_done[item] = t1;
+        __threadfence_block();
+        const int k = atomicAdd(&q_tail, 1);
+        atomicExch(&q_ring[k % kBalQueue], item);
+      }
+    }
+  }
 }
 
 // ARWMH.init (python/kernels/arwmh.py:111-136): q0 ~ U(-r, r)^d (unless given), U0, loc = q0, scale = I, ...

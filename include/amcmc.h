@@ -126,7 +126,9 @@ typedef struct amcmc_run_args {
   uint8_t* out_accept;     /* [n_steps][C] accept decisions, or NULL (parity tests) */
   int32_t kernel_kind;     /* amcmc_kernel_kind */
   int32_t impl;            /* 0 = auto; 1 = thread-per-chain registers; 2 = block-per-chain smem; 3 = tcgen05
-                            * (DIAMONDS, fp32, ARWMH with adapt = 1: auto picks tcgen05 above two chains per SM) */
+                            * (DIAMONDS, fp32, ARWMH with adapt = 1: auto picks tcgen05 above two chains per SM);
+                            * 4 = thread-per-chain registers behind a per-SM work queue (fp32 ARWMH; same trajectories as 1,
+                            * auto picks it when the chains give the schedulers an uneven number of warps) */
 } amcmc_run_args;
 
 /* ARWMH.init (arwmh.py:84-138).  If use_given_z == 0 draws q0 ~ U(-init_radius, init_radius)^d

@@ -213,3 +213,49 @@ def test_torch_custom_ops_wrap_the_c_abi():
                                         True, b2.seed, b2.chain_offset, _lib.KERNEL_ARWMH, _lib.IMPL_AUTO)
     assert torch.equal(oz, raw["z"]) and torch.equal(ope, raw["potential_energy"])
     assert torch.equal(b1.z, b2.z) and torch.equal(b1.scale, b2.scale) and torch.equal(b1.lam, b2.lam)
+
+
+# ---- thread-per-chain kernel behind the per-SM work queue (arwmh_small_balanced_kernel) ---------------------------------
+
+@pytest.mark.parametrize("model,Cn,T,thin,cs", [("eight_schools", 4736 * 3 + 17, 333, 7, 0), ("eight_schools", 1000, 1200, 50, 100),
+                                              ("kidiq", 9000, 257, 1, 3), ("eight_schools", 33, 40, 40, 0)])
+@pytest.mark.parametrize("adapt", [True, False])
+def test_balanced_register_kernel_is_bit_identical_to_the_plain_one(model, Cn, T, thin, cs, adapt):
+    """impl = 4 (16 worker warps per SM pop (chain group, segment) items; registers parked raw in shared memory between
+    segments) against impl = 1 (a warp owns its chains for the launch): same Philox stream, same arithmetic, so every output
+    -- samples, energies, accept decisions, final state incl. as_change -- must be EQUAL, for ragged chain counts (last group
+    partial, last CTAs one group short), segment boundaries off the collection points, and the frozen template."""
+    pot_model = getattr(models, model)
+    outs = []
+    for impl in (_lib.IMPL_REGISTER, _lib.IMPL_REGISTER_BALANCED):
+        s = am.ARWMH(pot_model, num_chains=Cn)
+        s.impl = impl
+        kw = dict(model_kwargs=models.synthetic_kidiq()) if model == "kidiq" else {}
+        st = s.init(11, num_warmup=100, init_params=None, **kw)
+        b = s._batch_from_state(st)
+        if not adapt:   # a non-trivial frozen state: adapt for a while first (plain kernel), then freeze
+            s.impl = _lib.IMPL_REGISTER
+            s.run_batch(b, 150, collect=())
+            s.impl = impl
+        raw = s.run_batch(b, T, thinning=thin, collect_start=cs, record_accept=True, adapt=adapt)
+        outs.append({**{k: v.clone() for k, v in raw.items()}, **{f: getattr(b, f).clone() for f in b._FIELDS}})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def test_balanced_kernel_is_the_default_at_the_headline_size_and_refuses_what_does_not_fit():
+    s = am.ARWMH(models.eight_schools, num_chains=64, dtype=torch.float64)
+    s.impl = _lib.IMPL_REGISTER_BALANCED
+    st = s.init(0, num_warmup=0, init_params=None)
+    with pytest.raises(RuntimeError, match="balanced"):
+        s.run_batch(s._batch_from_state(st), 10)
+    # 65,536 chains: auto = balanced (13.8 groups per SM); equal to the forced plain kernel
+    res = []
+    for impl in (_lib.IMPL_AUTO, _lib.IMPL_REGISTER):
+        s = am.ARWMH(models.eight_schools, num_chains=65536)
+        s.impl = impl
+        b = s._batch_from_state(s.init(3, num_warmup=50, init_params=None))
+        raw = s.run_batch(b, 300, thinning=50)
+        res.append((raw["z"].clone(), b.scale.clone(), b.asc.clone()))
+    for x, y in zip(*res):
+        assert torch.equal(x, y)
