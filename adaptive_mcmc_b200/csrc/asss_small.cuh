@@ -179,16 +179,15 @@ AMCMC_HD void asss_philox_head(const Philox& g, uint64_t step, R (&vn)[D + 1], R
   u_th = (R)word_to_uniform(w[2 * NPAIR + 1]);
 }
 
+// Steps [t0, t1) of the launch for one chain whose state is in `s`; any split of [0, n_steps) into consecutive ranges gives
+// the same trajectory and samples (the balanced launch of arwmh_small.cuh hands chains from warp to warp between ranges).
 template <class Model, typename R, bool EXTERNAL, bool ADAPT>
-AMCMC_HD void asss_chain_run(const Model& m, const StateView<R>& st, const RunView<R>& a, int64_t c) {
+AMCMC_HD void asss_chain_range(ChainRegs<R, Model::D>& s, const Model& m, const RunView<R>& a, const Philox& rng, int64_t C,
+                               int64_t c, int64_t t0, int64_t t1) {
   constexpr int D = Model::D;
-  const int64_t C = st.C;
-  ChainRegs<R, D> s;
-  load_chain(s, st, c);
-  const Philox rng(a.seed, (uint64_t)(c + a.chain_offset));
-  int64_t until_collect = a.collect_start + a.thinning;
-  int64_t sidx = 0;
-  for (int64_t t = 0; t < a.n_steps; ++t) {
+  int64_t sidx = t0 > a.collect_start ? (t0 - a.collect_start) / a.thinning : 0;  // samples taken before this range
+  int64_t until_collect = a.collect_start + (sidx + 1) * a.thinning - t0;
+  for (int64_t t = t0; t < t1; ++t) {
     const int64_t i = a.i0 + t;
     R vn[D + 1], u_t, u_th;
     if (EXTERNAL) {
@@ -220,8 +219,25 @@ AMCMC_HD void asss_chain_run(const Model& m, const StateView<R>& st, const RunVi
       ++sidx;
     }
   }
+}
+
+template <class Model, typename R, bool EXTERNAL, bool ADAPT>
+AMCMC_HD void asss_chain_run(const Model& m, const StateView<R>& st, const RunView<R>& a, int64_t c) {
+  constexpr int D = Model::D;
+  ChainRegs<R, D> s;
+  load_chain(s, st, c);
+  const Philox rng(a.seed, (uint64_t)(c + a.chain_offset));
+  asss_chain_range<Model, R, EXTERNAL, ADAPT>(s, m, a, rng, st.C, c, 0, a.n_steps);
   store_chain<R, D, ADAPT>(s, st, c);
 }
+
+// range runner for arwmh_small_balanced_kernel
+template <class Model, typename R, bool ADAPT, bool EXTERNAL> struct AsssRange {
+  static AMCMC_HD void run(ChainRegs<R, Model::D>& s, const Model& m, const RunView<R>& a, const Philox& rng, int64_t C, int64_t c,
+                           int64_t t0, int64_t t1) {
+    asss_chain_range<Model, R, EXTERNAL, ADAPT>(s, m, a, rng, C, c, t0, t1);
+  }
+};
 
 #ifdef __CUDACC__
 template <class Model, typename R, bool EXTERNAL, bool ADAPT>

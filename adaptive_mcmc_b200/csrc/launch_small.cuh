@@ -49,16 +49,6 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
   const int block = 64;
   const unsigned grid = (unsigned)((st->n_chains + block - 1) / block);
   const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
-  if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
-    if (a->adapt) {
-      if (ext) asss_small_kernel<Model, R, true, true><<<grid, block, 0, s>>>(m, sv, rv);
-      else     asss_small_kernel<Model, R, false, true><<<grid, block, 0, s>>>(m, sv, rv);
-    } else {  // frozen adapt_state: ASSS.sample_Pnx (asss.py:279-315)
-      if (ext) asss_small_kernel<Model, R, true, false><<<grid, block, 0, s>>>(m, sv, rv);
-      else     asss_small_kernel<Model, R, false, false><<<grid, block, 0, s>>>(m, sv, rv);
-    }
-    return check_cuda(cudaGetLastError(), "asss_small_kernel launch");
-  }
   // Balanced variant (arwmh_small.cuh): when the chains give every scheduler more than ~2 warps but not a whole number of
   // them, one 16-warp CTA per SM with a work queue keeps all schedulers saturated.  AMCMC_SMALL_BALANCED=0 forces the plain
   // kernel, =1 the balanced one wherever it fits (tests run both).
@@ -72,7 +62,10 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
     const size_t slot_bytes = (size_t)ChainSlot<R, Model::D>::NREG * 32 * sizeof(R);
     const size_t smem = (size_t)per_cta * slot_bytes;
     const bool fits = sizeof(R) == 4 && per_cta <= kBalQueue && smem <= 200 * 1024 && a->n_steps > 0;
-    const bool want = a->impl == 4 ? true : a->impl == 1 ? false : forced >= 0 ? forced != 0 : (per_cta >= 8 && per_cta % 4 != 0);
+    // auto: ARWMH only (the ASSS step spills more under the 512-thread register cap than it gains: 5.4e9 against 6.7e9
+    // chain-steps/s at 65,536 chains) and launches long enough to amortise the hand-offs
+    const bool want = a->impl == 4 ? true : a->impl == 1 ? false : forced >= 0 ? forced != 0
+                      : (per_cta >= 8 && per_cta % 4 != 0 && a->kernel_kind != AMCMC_KERNEL_ASSS && a->n_steps >= 128);
     if (a->impl == 4 && !fits) {
       set_error("amcmc_arwmh_run: the balanced thread-per-chain kernel needs fp32 and at most %d groups of 32 chains per SM within 200 KB of shared memory", kBalQueue);
       return AMCMC_ERR_UNSUPPORTED;
@@ -82,14 +75,20 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
       int64_t seg64 = a->n_steps / 64;  // ~64 hand-offs per group and launch: the tail imbalance is ~1 segment
       if (seg64 < 16) seg64 = 16;
       if (seg64 > 512) seg64 = 512;
-      const int seg = (int)seg64;
+      static const int seg_env = [] { const char* e = getenv("AMCMC_SMALL_BALANCED_SEG"); return e ? atoi(e) : 0; }();  // tuning knob
+      const int seg = seg_env > 0 ? seg_env : (int)seg64;
       int rc = 0;
       auto go = [&](auto kern) {
         if (smem > 48 * 1024) rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(balanced)");
         if (!rc) kern<<<bgrid, 32 * kBalWarps, smem, s>>>(m, sv, rv, n_groups, seg);
       };
-      if (a->adapt) { if (ext) go(arwmh_small_balanced_kernel<Model, R, true, true>); else go(arwmh_small_balanced_kernel<Model, R, true, false>); }
-      else { if (ext) go(arwmh_small_balanced_kernel<Model, R, false, true>); else go(arwmh_small_balanced_kernel<Model, R, false, false>); }
+      if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
+        if (a->adapt) { if (ext) go(arwmh_small_balanced_kernel<Model, R, true, AsssRange<Model, R, true, true>>); else go(arwmh_small_balanced_kernel<Model, R, true, AsssRange<Model, R, true, false>>); }
+        else { if (ext) go(arwmh_small_balanced_kernel<Model, R, false, AsssRange<Model, R, false, true>>); else go(arwmh_small_balanced_kernel<Model, R, false, AsssRange<Model, R, false, false>>); }
+      } else {
+        if (a->adapt) { if (ext) go(arwmh_small_balanced_kernel<Model, R, true, ArwmhRange<Model, R, true, true>>); else go(arwmh_small_balanced_kernel<Model, R, true, ArwmhRange<Model, R, true, false>>); }
+        else { if (ext) go(arwmh_small_balanced_kernel<Model, R, false, ArwmhRange<Model, R, false, true>>); else go(arwmh_small_balanced_kernel<Model, R, false, ArwmhRange<Model, R, false, false>>); }
+      }
       if (rc) return rc;
       return check_cuda(cudaGetLastError(), "arwmh_small_balanced_kernel launch");
     }
@@ -97,6 +96,16 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
   if (a->impl == 4) {
     set_error("amcmc_arwmh_run: the balanced thread-per-chain kernel is built for fp32");
     return AMCMC_ERR_UNSUPPORTED;
+  }
+  if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
+    if (a->adapt) {
+      if (ext) asss_small_kernel<Model, R, true, true><<<grid, block, 0, s>>>(m, sv, rv);
+      else     asss_small_kernel<Model, R, false, true><<<grid, block, 0, s>>>(m, sv, rv);
+    } else {  // frozen adapt_state: ASSS.sample_Pnx (asss.py:279-315)
+      if (ext) asss_small_kernel<Model, R, true, false><<<grid, block, 0, s>>>(m, sv, rv);
+      else     asss_small_kernel<Model, R, false, false><<<grid, block, 0, s>>>(m, sv, rv);
+    }
+    return check_cuda(cudaGetLastError(), "asss_small_kernel launch");
   }
   if (a->adapt) {
     if (ext) arwmh_small_kernel<Model, R, true, true><<<grid, block, 0, s>>>(m, sv, rv);

@@ -243,6 +243,24 @@ def test_balanced_register_kernel_is_bit_identical_to_the_plain_one(model, Cn, T
         assert torch.equal(outs[0][k], outs[1][k]), k
 
 
+@pytest.mark.parametrize("Cn,T,thin,cs,adapt", [(4736 * 2 + 5, 150, 7, 3, True), (1500, 90, 30, 0, False)])
+def test_balanced_kernel_runs_asss_bit_identically(Cn, T, thin, cs, adapt):
+    """the slice sampler through the same work queue (asss_chain_range): equal outputs for impl 1 and 4"""
+    outs = []
+    for impl in (_lib.IMPL_REGISTER, _lib.IMPL_REGISTER_BALANCED):
+        s = am.ASSS(models.eight_schools, num_chains=Cn)
+        s.impl = impl
+        b = s._batch_from_state(s.init(4, num_warmup=40, init_params=None))
+        if not adapt:
+            s.impl = _lib.IMPL_REGISTER
+            s.run_batch(b, 60, collect=())
+            s.impl = impl
+        raw = s.run_batch(b, T, thinning=thin, collect_start=cs, adapt=adapt)
+        outs.append({**{k: v.clone() for k, v in raw.items()}, **{f: getattr(b, f).clone() for f in b._FIELDS}})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
 def test_balanced_kernel_is_the_default_at_the_headline_size_and_refuses_what_does_not_fit():
     s = am.ARWMH(models.eight_schools, num_chains=64, dtype=torch.float64)
     s.impl = _lib.IMPL_REGISTER_BALANCED
