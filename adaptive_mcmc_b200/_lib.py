@@ -98,6 +98,7 @@ EXPORTED_SYMBOLS = (
     "amcmc_pooled_stats",
     "amcmc_pooled_update",
     "amcmc_selftest_umma",
+    "amcmc_host_chunk_samples",
     "amcmc_eval_kernel_sum",
     "amcmc_eval_mmd_sums",
     "amcmc_eval_sqdist_median",
@@ -162,6 +163,8 @@ def lib():
     L.amcmc_eval_kernel_sum.restype = C.c_int
     L.amcmc_eval_kernel_sum.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int,
                                         C.POINTER(C.c_double), C.c_void_p]
+    L.amcmc_host_chunk_samples.restype = C.c_int64
+    L.amcmc_host_chunk_samples.argtypes = [C.c_int64, C.c_int64]
     L.amcmc_eval_mmd_sums.restype = C.c_int
     L.amcmc_eval_mmd_sums.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_void_p]
     L.amcmc_eval_sqdist_median.restype = C.c_int

@@ -344,6 +344,17 @@ int amcmc_arwmh_init_host(amcmc_model* m, amcmc_state* hst, uint64_t seed, int64
 // *hst / *ha are host memory (pinned memory makes the copies truly asynchronous).  The run is cut
 // into chunks of whole thinning periods; chunk k's samples travel device->host on a second stream
 // while chunk k+1 computes, so the PCIe/C2C copy of the sample stream hides behind the kernel.
+int64_t amcmc_host_chunk_samples(int64_t remaining, int64_t thinning) {
+  if (remaining <= 0 || thinning < 1) return 0;
+  const int64_t lo = (128 + thinning - 1) / thinning, hi = (2048 + thinning - 1) / thinning;
+  if (remaining <= lo) return remaining;
+  int64_t ns = (remaining + 1) / 2;
+  if (ns < lo) ns = lo;
+  if (ns > hi) ns = hi;
+  if (remaining - ns < lo) ns = remaining;  // no stub chunk at the end
+  return ns;
+}
+
 int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args* ha) {
   int rc = validate_run(m, hst, ha);
   if (rc) return rc;
@@ -357,10 +368,12 @@ int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args*
   const int64_t nrm_per_step = (ha->kernel_kind == AMCMC_KERNEL_ASSS) ? d + 1 : d;
   const int64_t uni_per_step = (ha->kernel_kind == AMCMC_KERNEL_ASSS) ? 52 : 1;
   const bool want_z = ha->out_z && S > 0, want_pe = ha->out_potential_energy && S > 0;
-  // chunking: ~512 iterations per chunk, whole thinning periods, at most S samples.  The copy of the LAST chunk cannot hide
-  // behind a kernel, so chunks are kept short (at 65,536 eight_schools chains: 0.5 ms of exposed copy instead of 2.1 ms with
-  // 2048-iteration chunks; the ~20 extra launches per 10,000 iterations cost ~0.2 ms)
-  int64_t chunk_S = (want_z || want_pe) ? ((512 + thin - 1) / thin) : 0;
+  // chunking in whole thinning periods: every chunk takes half of the samples that remain, between ~128 and ~2048 iterations
+  // (amcmc_host_chunk_samples).  Long chunks first keep the launch boundaries few (each costs a state round trip through
+  // HBM and a ramp-down of the kernel, ~45 us at 65,536 eight_schools chains); the copy of the LAST chunk cannot hide behind
+  // a kernel, so the chunks taper: 41, 41, 41, 39, 19, 10, 5, 4 samples for 200 samples at thinning 50 (0.2 ms of exposed
+  // copy and 8 launches, against 0.5 ms and 20 launches with uniform 512-iteration chunks).
+  int64_t chunk_S = (want_z || want_pe) ? (2048 + thin - 1) / thin : 0;
   if (chunk_S > S) chunk_S = S;
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t b_vec = al((size_t)C * w), b_mat = al((size_t)C * d * w), b_tri = al((size_t)C * np * w);
@@ -416,7 +429,7 @@ int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* hst, const amcmc_run_args*
     amcmc_run_args da = *ha;
     int64_t steps, ns;
     if (chunk_S > 0 && s_done < S) {
-      ns = (S - s_done < chunk_S) ? (S - s_done) : chunk_S;
+      ns = amcmc_host_chunk_samples(S - s_done, thin);
       da.collect_start = (t_done == 0) ? ha->collect_start : 0;
       steps = da.collect_start + ns * thin;
       if (s_done + ns == S) steps = T - t_done;  // the last chunk also takes the uncollected tail

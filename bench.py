@@ -383,9 +383,12 @@ def run_ours(args):
             "d2h_GBps_per_rank": (state_bytes + S * (d + 1) * Cn * esz) * K / float(te.item()) / 1e9,
             "copy_probe": probe_copies(dev, world, local, quick=True),
         }
-        S_ = T // args.thinning
-        chunk_S = min(S_, (512 + args.thinning - 1) // args.thinning) or 1
-        launches += K * max(1, -(-S_ // chunk_S))
+        # launches of the host entry per step: its tapering chunk plan (amcmc_host_chunk_samples, csrc/capi.cu)
+        left, n_chunks = T // args.thinning, 0
+        while left > 0:
+            left -= int(_lib.lib().amcmc_host_chunk_samples(left, args.thinning))
+            n_chunks += 1
+        launches += K * max(1, n_chunks)
 
     extra = None
     thin1 = None

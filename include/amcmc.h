@@ -151,6 +151,11 @@ int amcmc_potential(const amcmc_model* m, int64_t n, const void* q, void* out, v
  * returning (this is what a non-CUDA caller, e.g. the reference's NumPy/JAX-CPU
  * scripts, would bind).  Device scratch is cached inside the model handle. */
 int amcmc_arwmh_run_host(amcmc_model* m, amcmc_state* host_state, const amcmc_run_args* host_args);
+/* The chunk plan of amcmc_arwmh_run_host: number of samples (thinning periods) the next launch collects when `remaining`
+ * samples are left -- half of them, between ceil(128 / thinning) and ceil(2048 / thinning), never leaving a shorter stub.
+ * The chain is bit-reproducible for a given plan (a launch boundary stores the proposal factor in the ABI's Cholesky form:
+ * one rounding), so a device-pointer caller that wants the host entry's exact numbers cuts its launches the same way. */
+int64_t amcmc_host_chunk_samples(int64_t remaining, int64_t thinning);
 /* amcmc_arwmh_init with HOST buffers in *host_state (same contract; synchronises before returning). */
 int amcmc_arwmh_init_host(amcmc_model* m, amcmc_state* host_state, uint64_t seed, int64_t chain_offset,
                           double init_radius, int use_given_z);

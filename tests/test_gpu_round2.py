@@ -35,7 +35,7 @@ def _host_state(batch, host):
     return hs
 
 
-@pytest.mark.parametrize("T", [7, 1300])  # 1300 > two 515-step chunks of the host entry: the chunk offsets matter
+@pytest.mark.parametrize("T", [7, 1300, 5003])  # several chunks of the host entry (260 samples: 130 + 65 + 33 + 32): the offsets matter
 def test_run_host_asss_external_draws(T):
     """The host-buffer entry point must size and offset the external draws by the sampler kind: ASSS reads
     normals[T][d+1][C] and uniforms[T][52][C] (include/amcmc.h).  Bit-identical to the device-pointer path."""
@@ -48,12 +48,14 @@ def test_run_host_asss_external_draws(T):
     nrm = torch.randn(T, Cn, d + 1, generator=g)
     uni = torch.rand(T, Cn, 52, generator=g)
     dn, du = s._draws_to_device_layout((nrm, uni))  # [T][d+1][C], [T][52][C]
-    # the host entry cuts the run into chunks of ceil(512 / thinning) samples; a launch boundary converts the carried
+    # the host entry cuts the run into tapering chunks (amcmc_host_chunk_samples); a launch boundary converts the carried
     # LDL^T factor to the ABI's Cholesky form and back (a rounding), so the device-pointer run is cut at the same steps
-    zs, pes, t0 = [], [], 0
+    zs, pes, t0, s_left = [], [], 0, T // 5
     while t0 < T:
-        n = min(103 * 5, T - t0)
-        if T - t0 - n < 5:  # the last chunk also takes the uncollected tail
+        ns = _lib.lib().amcmc_host_chunk_samples(s_left, 5) if s_left else 0
+        n = ns * 5
+        s_left -= ns
+        if s_left == 0:  # the last chunk also takes the uncollected tail
             n = T - t0
         raw = s.run_batch(b, n, thinning=5, draws=(dn[t0:t0 + n].contiguous(), du[t0:t0 + n].contiguous()))
         zs.append(raw["z"]); pes.append(raw["potential_energy"])
