@@ -325,18 +325,27 @@ arwmh_small_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Balanced variant: one 16-warp CTA per SM, warps take (chain group, segment of steps) items from a queue.
+// Balanced variant: one CTA of 12 worker warps per SM; the warps take (chain group, segment of steps) items from a queue.
 //
 // A warp of arwmh_small_kernel owns its 32 chains for the whole launch, so the number of warps per scheduler is fixed by the
 // chain count: 65,536 chains on 148 SMs are 13.8 warps per SM = 4 + 4 + 3 + 3 per scheduler, and the launch lasts as long as
 // the schedulers with 4 (measured, chain-steps/s at 1 / 2 / 3 / 3.5 / 4 warps per scheduler: 2.60 / 3.63 / 3.74 / 3.33 / 3.80
 // x 10^10 -- a scheduler is saturated from 2 warps on, and 65,536 chains take exactly as long as 75,776).  Here every SM runs
-// 16 worker warps (4 per scheduler) over its ~14 groups of 32 chains: a worker pops a group, runs `seg` steps with the state
-// in registers, parks the registers (bit for bit, no LDL^T <-> Cholesky conversion) in the group's shared-memory slot and
-// pushes the group back.  All four schedulers stay saturated until the SM's work is done: 14/16 of the time.  The
-// trajectories do not depend on the schedule (counter RNG, raw register hand-off).
+// 12 worker warps (3 per scheduler, always busy) over its ~14 groups of 32 chains: a worker pops a group, runs `seg` steps
+// with the state in registers, parks the registers (bit for bit, no LDL^T <-> Cholesky conversion) in the group's
+// shared-memory slot and pushes the group back.  All four schedulers stay saturated until the SM's work is done.  The
+// trajectories do not depend on the schedule (counter RNG, raw register hand-off).  Workers per SM, measured at 65,536 chains:
+// 8 (255 registers) 3.55e10, 12 (168 registers, no spills) 3.82e10, 16 (128 registers) 3.77e10 chain-steps/s; the ASSS step
+// (asss_small.cuh) needs more registers: 8 workers 7.85e9, 12 workers 7.64e9, plain kernel 6.88e9.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBalWarps = 16;
+#ifndef AMCMC_BAL_WARPS
+#define AMCMC_BAL_WARPS 12
+#endif
+constexpr int kBalWarps = AMCMC_BAL_WARPS;
+#ifndef AMCMC_BAL_WARPS_ASSS
+#define AMCMC_BAL_WARPS_ASSS 8
+#endif
+constexpr int kBalWarpsAsss = AMCMC_BAL_WARPS_ASSS;
 constexpr int kBalQueue = 32;  // ring capacity >= groups per CTA
 
 template <typename R, int D> struct ChainSlot {
@@ -381,8 +390,8 @@ template <class Model, typename R, bool ADAPT, bool EXTERNAL> struct ArwmhRange 
   }
 };
 
-template <class Model, typename R, bool ADAPT, class Runner>
-__global__ void __launch_bounds__(32 * kBalWarps, 1)
+template <class Model, typename R, bool ADAPT, class Runner, int WARPS = kBalWarps>
+__global__ void __launch_bounds__(32 * WARPS, 1)
 arwmh_small_balanced_kernel(const Model m, const StateView<R> st, const RunView<R> a, int64_t n_groups, int seg) {
   constexpr int D = Model::D;
   using Slot = ChainSlot<R, D>;

@@ -50,7 +50,7 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
   const unsigned grid = (unsigned)((st->n_chains + block - 1) / block);
   const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
   // Balanced variant (arwmh_small.cuh): when the chains give every scheduler more than ~2 warps but not a whole number of
-  // them, one 16-warp CTA per SM with a work queue keeps all schedulers saturated.  AMCMC_SMALL_BALANCED=0 forces the plain
+  // them, one CTA of 12 worker warps per SM with a work queue keeps all schedulers saturated.  AMCMC_SMALL_BALANCED=0 forces the plain
   // kernel, =1 the balanced one wherever it fits (tests run both).
   if constexpr (sizeof(R) == 4) {
     static const int forced = [] { const char* e = getenv("AMCMC_SMALL_BALANCED"); return e ? atoi(e) : -1; }();
@@ -62,10 +62,9 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
     const size_t slot_bytes = (size_t)ChainSlot<R, Model::D>::NREG * 32 * sizeof(R);
     const size_t smem = (size_t)per_cta * slot_bytes;
     const bool fits = sizeof(R) == 4 && per_cta <= kBalQueue && smem <= 200 * 1024 && a->n_steps > 0;
-    // auto: ARWMH only (the ASSS step spills more under the 512-thread register cap than it gains: 5.4e9 against 6.7e9
-    // chain-steps/s at 65,536 chains) and launches long enough to amortise the hand-offs
+    // auto: launches long enough to amortise the hand-offs, and a group count per SM that the plain kernel cannot spread evenly
     const bool want = a->impl == 4 ? true : a->impl == 1 ? false : forced >= 0 ? forced != 0
-                      : (per_cta >= 8 && per_cta % 4 != 0 && a->kernel_kind != AMCMC_KERNEL_ASSS && a->n_steps >= 128);
+                      : (per_cta >= 8 && per_cta % 4 != 0 && a->n_steps >= 128);
     if (a->impl == 4 && !fits) {
       set_error("amcmc_arwmh_run: the balanced thread-per-chain kernel needs fp32 and at most %d groups of 32 chains per SM within 200 KB of shared memory", kBalQueue);
       return AMCMC_ERR_UNSUPPORTED;
@@ -78,13 +77,15 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
       static const int seg_env = [] { const char* e = getenv("AMCMC_SMALL_BALANCED_SEG"); return e ? atoi(e) : 0; }();  // tuning knob
       const int seg = seg_env > 0 ? seg_env : (int)seg64;
       int rc = 0;
+      int workers = kBalWarps;
       auto go = [&](auto kern) {
         if (smem > 48 * 1024) rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(balanced)");
-        if (!rc) kern<<<bgrid, 32 * kBalWarps, smem, s>>>(m, sv, rv, n_groups, seg);
+        if (!rc) kern<<<bgrid, 32 * workers, smem, s>>>(m, sv, rv, n_groups, seg);
       };
       if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
-        if (a->adapt) { if (ext) go(arwmh_small_balanced_kernel<Model, R, true, AsssRange<Model, R, true, true>>); else go(arwmh_small_balanced_kernel<Model, R, true, AsssRange<Model, R, true, false>>); }
-        else { if (ext) go(arwmh_small_balanced_kernel<Model, R, false, AsssRange<Model, R, false, true>>); else go(arwmh_small_balanced_kernel<Model, R, false, AsssRange<Model, R, false, false>>); }
+        workers = kBalWarpsAsss;  // 8 workers = 2 per scheduler: 255 registers per thread, the slice-sampling step does not spill
+        if (a->adapt) { if (ext) go(arwmh_small_balanced_kernel<Model, R, true, AsssRange<Model, R, true, true>, kBalWarpsAsss>); else go(arwmh_small_balanced_kernel<Model, R, true, AsssRange<Model, R, true, false>, kBalWarpsAsss>); }
+        else { if (ext) go(arwmh_small_balanced_kernel<Model, R, false, AsssRange<Model, R, false, true>, kBalWarpsAsss>); else go(arwmh_small_balanced_kernel<Model, R, false, AsssRange<Model, R, false, false>, kBalWarpsAsss>); }
       } else {
         if (a->adapt) { if (ext) go(arwmh_small_balanced_kernel<Model, R, true, ArwmhRange<Model, R, true, true>>); else go(arwmh_small_balanced_kernel<Model, R, true, ArwmhRange<Model, R, true, false>>); }
         else { if (ext) go(arwmh_small_balanced_kernel<Model, R, false, ArwmhRange<Model, R, false, true>>); else go(arwmh_small_balanced_kernel<Model, R, false, ArwmhRange<Model, R, false, false>>); }
