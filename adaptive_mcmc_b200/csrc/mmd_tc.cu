@@ -16,11 +16,15 @@
 //              ex2.approx.ftz(fma(acc, 2 gamma log2e, na_i + nb_j)), fp32 partial sums per pair, float64 per thread over the launch
 // An A stage (operand + norms) and its accumulator are released together by the epilogue, so the MMA of pair t + 1 overlaps the
 // epilogue of pair t and the load of pair t + 2 starts when that epilogue ends.  The epilogue is bounded by MUFU (one ex2 per
-// pair of points, 16 per clock per SM = 2,048 cycles per tile pair); measured 4.0k cycles per tile pair at n = m = 40,000
-// (2.3e12 kernel values/s, 0.51 of the MUFU bound): the load + MMA of pair t + 2 (~2.2k cycles of latency) is exposed behind the
-// epilogue of pair t + 1 -- a deeper A ring with its own release barrier would hide it (not built: the three sums at 10^4 points
-// already take 0.21 ms per call, launch overheads included, against 1.74 ms for the three CUDA-core passes of eval.cu).
+// pair of points, 16 per clock per SM = 2,048 cycles per tile pair).  clock64 build (-DAMCMC_MMD_TIMING), n = m = 40,000:
+// 3.15k cycles per tile pair = 226 waiting for the accumulator + 180 for the first TMEM load + 2,620 in the exp loop + 130
+// hand-back: 0.65 of the MUFU bound, 0.78 inside the exp loop.  A 4-deep A ring with its own release barriers was built and
+// measured: no faster (the loads were never exposed; the extra bookkeeping cost 10 %) -- what remains is that all 16 epilogue
+// warps wait for the same accumulator at the same time; 128-column accumulators (four in flight) would let them stagger.
+// The three sums at 10^4 points take 0.21 ms per call, launch overheads included, against 1.74 ms for the three CUDA-core
+// passes of eval.cu.
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include "internal.h"
 #include "tc_common.cuh"
@@ -199,6 +203,9 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mmd_tc_kernel(const MmdParams p
     const int part_col = ((warp - 2) >> 2) * MT_EPI_COLS;  // first of this warp's columns
     const int row = quarter * 32 + lane;
     double tot0 = 0.0, tot1 = 0.0, tot2 = 0.0;
+#ifdef AMCMC_MMD_TIMING
+    long long tk[4] = {0, 0, 0, 0};
+#endif
     int it = 0, cur_b = -1, bbuf = 1;
     for (int64_t q = q_begin; q < q_end; ++q, ++it) {
       const int s = it & 1;
@@ -207,9 +214,16 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mmd_tc_kernel(const MmdParams p
       if (bkey != cur_b) { cur_b = bkey; bbuf ^= 1; }
       const float* nA = reinterpret_cast<const float*>(smem + s * MT_STAGE + MT_A_BYTES);
       const float* nB = reinterpret_cast<const float*>(smem + MT_OFF_B + bbuf * MT_BBUF + MT_B_BYTES) + part_col;
+#ifdef AMCMC_MMD_TIMING  // clock64 breakdown of the epilogue (profiles/r02_eval.md)
+      long long tl = clock64();
+#define MT_T(k) { const long long c_ = clock64(); tk[k] += c_ - tl; tl = c_; }
+#else
+#define MT_T(k)
+#endif
       mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));  // the norms came with the same TMA transaction (already complete here)
       mbar_wait(&acc_full[s], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      MT_T(0)
       const float na = nA[row];
       const int64_t gi = (int64_t)pi.ta * MT_M + row, gj0 = (int64_t)pi.tb * MT_N + part_col;
       // same-sample problems skip i == j: only tile pairs that touch the diagonal take the compare
@@ -221,6 +235,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mmd_tc_kernel(const MmdParams p
 #pragma unroll
       for (int ch = 0; ch < MT_EPI_COLS / 32; ++ch) {
         tmem_ld_wait();
+        MT_T(1)
         if (ch + 1 < MT_EPI_COLS / 32) tmem_ld_32x32(tbase + (uint32_t)((ch + 1) * 32), v[(ch + 1) & 1]);
         const float(&w)[32] = v[ch & 1];
 #pragma unroll
@@ -239,6 +254,7 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mmd_tc_kernel(const MmdParams p
           }
           part += (e0 + e1) + (e2 + e3);
         }
+        MT_T(2)
       }
       tc_fence_before();
       __syncwarp();
@@ -246,7 +262,13 @@ __global__ void __launch_bounds__(MT_THREADS, 1) mmd_tc_kernel(const MmdParams p
       tot0 += pi.prob == 0 ? (double)part : 0.0;
       tot1 += pi.prob == 1 ? (double)part : 0.0;
       tot2 += pi.prob == 2 ? (double)part : 0.0;
+      MT_T(3)
     }
+#ifdef AMCMC_MMD_TIMING
+    if (blockIdx.x == 0 && tid == 64 && it > 0)
+      printf("[mmd] %d pairs: wait acc_full %lld, wait tmem ld %lld, exp %lld, tail %lld cycles per pair\n", it, tk[0] / it, tk[1] / it,
+             tk[2] / it, tk[3] / it);
+#endif
     for (int o = 16; o; o >>= 1) {
       tot0 += __shfl_xor_sync(0xffffffffu, tot0, o);
       tot1 += __shfl_xor_sync(0xffffffffu, tot1, o);
