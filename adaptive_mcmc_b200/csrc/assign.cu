@@ -11,6 +11,7 @@
 // One round = three small kernels (bid / resolve / assign); HBM-bound: a bidding row streams its n int32 costs once
 // (coalesced 16-byte loads) against the n prices, which stay in L2.  No host round trip inside a phase except the
 // unassigned-rows counter, read back every few rounds.
+#include <cooperative_groups.h>
 #include <climits>
 #include <cstring>
 #include <cstdint>
@@ -277,6 +278,103 @@ auction_tail_kernel(const int32_t* __restrict__ ci, int n, long long* price_g, v
   if (threadIdx.x == 0) atomicAdd(bids_done, (unsigned long long)done);
 }
 
+// ---- the same tail on a thread-block cluster ------------------------------------------------------------------------------
+// One SM issues ~0.45 instructions per cycle and scheduler on the dependent top-2 chains, so the single-CTA tail is bound by
+// its own instruction stream (profiles/r02_eval.md).  Here a cluster of 8 CTAs splits the columns: CTA r keeps the prices of
+// its slice in shared memory and scans only that slice of the bidder's row; the eight partial results are exchanged through
+// distributed shared memory (every CTA writes its partial into every CTA's exchange slot, one cluster barrier per bid, two
+// slot sets alternate) and every CTA merges them, so all CTAs carry identical copies of the queue and of the column owners
+// and run the same control flow.  Rank 0 writes the global side (col_of, the unassigned counter).  10^4 x 10^4: 0.19 s against
+// 0.23-0.25 s with the single CTA (~1.9 us per bid: HBM latency of the row, two block barriers, one cluster barrier);
+// prefetching the rows of the eight local winners' owners into L2 during the exchange was measured: 0.23 s, not kept.
+constexpr int kClu = 8;
+constexpr int kCluThreads = 512;
+
+__global__ void __cluster_dims__(kClu, 1, 1) __launch_bounds__(kCluThreads)
+auction_tail_cluster_kernel(const int32_t* __restrict__ ci, int n, long long* price_g, int* col_of, int* row_of_g, long long eps,
+                            int* __restrict__ n_unassigned, long long max_bids, unsigned long long* __restrict__ bids_done) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  extern __shared__ long long clu_dyn[];
+  const int slice = (n + kClu - 1) / kClu;
+  const int c0 = rank * slice, c1 = min(n, c0 + slice);
+  long long* s_price = clu_dyn;                                   // [slice]
+  int* s_owner = reinterpret_cast<int*>(clu_dyn + slice);         // [n] replica
+  __shared__ Low2 xch[2][kClu];
+  __shared__ Low2 sh[kCluThreads / 32];
+  __shared__ int queue[kTailQueue];
+  __shared__ int q_count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the queue must be identical in every CTA: ordered compaction by one warp
+  if (warp == 0) {
+    int cnt = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const bool un = i < n && col_of[i] < 0;
+      const unsigned m = __ballot_sync(0xffffffffu, un);
+      if (un) {
+        const int k = cnt + __popc(m & ((1u << lane) - 1u));
+        if (k < kTailQueue) queue[k] = i;
+      }
+      cnt += __popc(m);
+    }
+    if (lane == 0) q_count = cnt;
+  }
+  for (int j = threadIdx.x; j < n; j += kCluThreads) s_owner[j] = row_of_g[j];
+  for (int j = c0 + threadIdx.x; j < c1; j += kCluThreads) s_price[j - c0] = price_g[j];
+  __syncthreads();
+  int nq = q_count;
+  if (nq > kTailQueue) return;  // every CTA takes the same decision (before any cluster barrier)
+  cluster.sync();               // all exchange slots exist before anybody writes into them
+  const unsigned int np1 = (unsigned int)n + 1u;
+  long long done = 0;
+  int par = 0;
+  while (nq > 0 && done < max_bids) {
+    const int i = queue[nq - 1];
+    const int32_t* row = ci + (int64_t)i * n;
+    Low2 t{kNoCost, kNoCost, INT_MAX};
+    for (int j = c0 + threadIdx.x; j < c1; j += kCluThreads) low2_push(t, (unsigned int)__ldcs(row + j), np1, (unsigned long long)s_price[j - c0], j);
+    t = warp_low2(t);
+    if (lane == 0) sh[warp] = t;
+    __syncthreads();
+    if (warp == 0) {
+      Low2 u = lane < kCluThreads / 32 ? sh[lane] : Low2{kNoCost, kNoCost, INT_MAX};
+      u = warp_low2(u);
+      if (lane < kClu) *cluster.map_shared_rank(&xch[par][rank], lane) = u;  // my partial into CTA `lane`
+    }
+    cluster.sync();
+    if (warp == 0) {
+      Low2 u = lane < kClu ? xch[par][lane] : Low2{kNoCost, kNoCost, INT_MAX};
+      u = warp_low2(u);
+      if (lane == 0) {
+        const int j = u.arg;
+        const int prev = s_owner[j];
+        const long long gap = u.second == kNoCost ? 0 : (long long)(u.second - u.best);
+        if (j >= c0 && j < c1) s_price[j - c0] += gap + eps;
+        s_owner[j] = i;
+        if (prev >= 0) queue[nq - 1] = prev;   // the evicted owner takes the slot of the popped row
+        else q_count = nq - 1;
+        if (rank == 0) {
+          col_of[i] = j;
+          if (prev >= 0) col_of[prev] = -1;
+          else atomicSub(n_unassigned, 1);
+        }
+      }
+    }
+    ++done;
+    par ^= 1;
+    __syncthreads();
+    nq = q_count;
+  }
+  cluster.sync();  // nobody leaves while a peer may still write into its exchange slots
+  for (int j = c0 + threadIdx.x; j < c1; j += kCluThreads) price_g[j] = s_price[j - c0];
+  if (rank == 0) {
+    for (int j = threadIdx.x; j < n; j += kCluThreads) row_of_g[j] = s_owner[j];
+    if (threadIdx.x == 0) atomicAdd(bids_done, (unsigned long long)done);
+  }
+}
+
 __global__ void auction_reset_kernel(int n, int* __restrict__ col_of, int* __restrict__ row_of, long long* __restrict__ maxbid,
                                      int* __restrict__ winner, int* __restrict__ n_unassigned) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,6 +397,22 @@ __global__ void assign_total_kernel(const int32_t* __restrict__ ci, const float*
   if ((threadIdx.x & 31) == 0) { atomicAdd(total_int, vi); atomicAdd(total_float, vf); }
 }
 
+// per-device workspace that grows on demand (calls on one device are expected from one host thread at a time, as for eval.cu)
+static char* assign_workspace(size_t need) {
+  static char* buf[64] = {};
+  static size_t cap[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (cap[dev] < need) {
+    if (buf[dev]) cudaFree(buf[dev]);
+    buf[dev] = nullptr;
+    cap[dev] = 0;
+    if (cudaMalloc(&buf[dev], need) != cudaSuccess) return nullptr;
+    cap[dev] = need;
+  }
+  return buf[dev];
+}
+
 }  // namespace amcmc
 
 using namespace amcmc;
@@ -318,7 +432,12 @@ extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* co
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t b_ci = quantised ? 0 : al((size_t)total * 4);
   const size_t bytes = b_ci + 3 * al((size_t)n * 8) + 4 * al((size_t)n * 4) + 256;
-  if ((rc = check_cuda(cudaMalloc(&buf, bytes), "cudaMalloc(assignment workspace)"))) return rc;
+  const bool cached = bytes <= ((size_t)1 << 30);  // up to 1 GiB stays allocated between calls (n <= ~16,000): a 400 MB
+  if (cached) {                                    // cudaMalloc / cudaFree pair per call costs up to hundreds of ms at times
+    buf = assign_workspace(bytes);
+    if (!buf) { set_error("amcmc_eval_assignment: workspace allocation failed"); return AMCMC_ERR_CUDA; }
+  } else if ((rc = check_cuda(cudaMalloc(&buf, bytes), "cudaMalloc(assignment workspace)"))) return rc;
+  auto release = [&]() { if (!cached) cudaFree(buf); };
   char* p = buf;
   auto take = [&](size_t b) { char* q = p; p += al(b); return (void*)q; };
   int32_t* ci = quantised ? quantised : (int32_t*)take((size_t)total * 4);
@@ -339,7 +458,14 @@ extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* co
   const unsigned nb = (unsigned)((n + 255) / 256);
   if (n <= kTailSmemCols && (size_t)n * 12 > 48 * 1024 &&
       (rc = check_cuda(cudaFuncSetAttribute(auction_tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTailSmemCols * 12),
-                       "cudaFuncSetAttribute(auction_tail_kernel)"))) { cudaFree(buf); return rc; }
+                       "cudaFuncSetAttribute(auction_tail_kernel)"))) { release(); return rc; }
+  // cluster tail: from ~2,000 columns on (below, one CTA scans a row in a few hundred cycles anyway); AMCMC_ASSIGN_CLUSTER=0/1 overrides
+  const size_t clu_smem = (size_t)((n + kClu - 1) / kClu) * 8 + (size_t)n * 4 + 16;
+  static const int clu_env = [] { const char* e = getenv("AMCMC_ASSIGN_CLUSTER"); return e ? atoi(e) : -1; }();
+  const bool use_cluster = (clu_env >= 0 ? clu_env != 0 : n >= 2048) && clu_smem <= 200 * 1024 && n >= kClu;
+  if (use_cluster && clu_smem > 48 * 1024 &&
+      (rc = check_cuda(cudaFuncSetAttribute(auction_tail_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)clu_smem),
+                       "cudaFuncSetAttribute(auction_tail_cluster_kernel)"))) { release(); return rc; }
   // epsilon-scaling on costs multiplied by (n + 1): start at ~1/8 of the largest scaled cost, divide by 6 down to 1
   long long eps = ((long long)16777215 * (n + 1)) / 8;
   if (eps < 1) eps = 1;
@@ -357,7 +483,9 @@ extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* co
       const bool tail = un <= kTailQueue / 2;
       if (dbg) cudaEventRecord(e0, s);
       if (tail) {  // few rows left: finish the phase in one CTA (Gauss-Seidel order)
-        if (n <= kTailSmemCols)
+        if (use_cluster)
+          auction_tail_cluster_kernel<<<kClu, kCluThreads, clu_smem, s>>>(ci, n, price, col_of, row_of, eps, n_un, (long long)1 << 22, tail_bids);
+        else if (n <= kTailSmemCols)
           auction_tail_kernel<true><<<1, kTailThreads, (size_t)n * 12, s>>>(ci, n, price, col_of, row_of, eps, n_un, (long long)1 << 22, tail_bids);
         else
           auction_tail_kernel<false><<<1, kTailThreads, 0, s>>>(ci, n, price, col_of, row_of, eps, n_un, (long long)1 << 22, tail_bids);
@@ -369,11 +497,11 @@ extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* co
         }
         rounds += 4;
       }
-      if ((rc = check_cuda(cudaMemcpyAsync(&un, n_un, 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync"))) { cudaFree(buf); return rc; }
+      if ((rc = check_cuda(cudaMemcpyAsync(&un, n_un, 4, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync"))) { release(); return rc; }
       if (dbg) cudaEventRecord(e1, s);
-      if ((rc = check_cuda(cudaStreamSynchronize(s), "auction round"))) { cudaFree(buf); return rc; }
+      if ((rc = check_cuda(cudaStreamSynchronize(s), "auction round"))) { release(); return rc; }
       if (dbg) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); if (tail) { ms_tail += ms; ++n_tail; } else ms_jac += ms; }
-      if (++host_iters > 2000000) { cudaFree(buf); set_error("amcmc_eval_assignment: auction did not terminate"); return AMCMC_ERR_CUDA; }
+      if (++host_iters > 2000000) { release(); set_error("amcmc_eval_assignment: auction did not terminate"); return AMCMC_ERR_CUDA; }
     }
     if (dbg) {
       unsigned long long tb = 0;
@@ -387,8 +515,8 @@ extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* co
   if (out_host) {
     assign_total_kernel<<<nb, 256, 0, s>>>(ci, cost, n, col_of, (unsigned long long*)(scal + 4), (double*)(scal + 6));
     unsigned int h[8];
-    if ((rc = check_cuda(cudaMemcpyAsync(h, scal, 32, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync"))) { cudaFree(buf); return rc; }
-    if ((rc = check_cuda(cudaStreamSynchronize(s), "assignment totals"))) { cudaFree(buf); return rc; }
+    if ((rc = check_cuda(cudaMemcpyAsync(h, scal, 32, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync"))) { release(); return rc; }
+    if ((rc = check_cuda(cudaStreamSynchronize(s), "assignment totals"))) { release(); return rc; }
     unsigned long long ti; double tf;
     memcpy(&ti, h + 4, 8); memcpy(&tf, h + 6, 8);
     unsigned long long tb = 0;
@@ -397,6 +525,6 @@ extern "C" int amcmc_eval_assignment(const float* cost, int64_t n64, int32_t* co
   }
   if (dbg) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
   rc = check_cuda(cudaGetLastError(), "amcmc_eval_assignment");
-  cudaFree(buf);
+  release();
   return rc;
 }
