@@ -213,7 +213,7 @@ auction_tail_kernel(const int32_t* __restrict__ ci, int n, long long* price_g, v
     long long tl = clock64();
 #endif
     const int i = queue[nq - 1];
-#ifdef AMCMC_ASSIGN_FIXROW
+#ifdef AMCMC_ASSIGN_FIXROW  // experiment only (WRONG results): rows aliased onto 64 L2-resident ones, to separate HBM latency from issue time
     const int32_t* row = ci + (int64_t)(i & 63) * n;
 #else
     const int32_t* row = ci + (int64_t)i * n;
