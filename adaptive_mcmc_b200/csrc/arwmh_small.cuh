@@ -248,7 +248,9 @@ AMCMC_HD void step_draws(const RunView<R>& a, const Philox& rng, int64_t C, int6
 }
 
 // Steps [t0, t1) of the launch without any collection logic: the hot loop.  (Generating the draws of step t + 1 next to
-// the sweep of step t -- software pipelining of the counter RNG -- was measured: 3.33e10 vs 3.36e10 chain-steps/s, not kept.)  n follows arwmh.py:180-181 (it restarts at
+// the sweep of step t -- software pipelining of the counter RNG -- was measured: 3.33e10 vs 3.36e10 chain-steps/s, and no change
+// of the few-chain latency either, 0.93 us per step for 1 to 100 chains: the step's own dependent chain is the critical path;
+// not kept.)  n follows arwmh.py:180-181 (it restarts at
 // 1 after the warm-up); the frozen kernel (sample_Pnx, pooled windows) averages its acceptance rate over THIS launch.
 template <class Model, typename R, bool ADAPT, bool EXTERNAL>
 AMCMC_HD void arwmh_steps(ChainRegs<R, Model::D>& s, const Model& m, const RunView<R>& a, const Philox& rng, int64_t C,
