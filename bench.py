@@ -262,8 +262,12 @@ def run_ours(args):
         return
     if args.workload in ("diamonds", "gaussian_ram"):  # secondary workload on its own (profiling, scaling runs)
         K, W = args.steps, max(args.warmup, 3)
+        clocks = ClockSampler(local)  # over the whole workload (warm-up included): these functions time themselves
+        if rank == 0:
+            clocks.start()
         res = (run_diamonds_tc if args.workload == "diamonds" else run_gaussian_ram)(args, world, rank, dev, K, W)
         if rank == 0:
+            res["clocks"] = clocks.stop()
             res.update({"n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True, "scaling": "weak",
                         "vs_baseline": None, "dtype": "bf16x3 split (fp32 accumulate)" if args.workload == "diamonds" else "f32",
                         "data": "synthetic",
