@@ -57,3 +57,25 @@ def test_no_oracle_import_in_product():
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
                 assert "liboracle" not in txt and "hostsim" not in txt.replace("tests/hostsim", ""), f
+
+
+@pytest.mark.parametrize("S,thin", [(200, 50), (260, 5), (1000, 5), (1, 50), (5, 50), (4096, 1), (7, 1000), (100000, 10)])
+def test_host_chunk_plan(built, S, thin):
+    """amcmc_host_chunk_samples (pure host function): the plan covers the S samples exactly, every launch is between
+    ceil(128 / thinning) and ceil(2048 / thinning) samples except that a short rest is absorbed instead of left as a stub,
+    and launches never grow -- long ones first, the one whose copy cannot hide last."""
+    from adaptive_mcmc_b200 import _lib
+
+    L = _lib.lib()
+    lo, hi = -(-128 // thin), -(-2048 // thin)
+    left, plan = S, []
+    while left:
+        n = int(L.amcmc_host_chunk_samples(left, thin))
+        assert 1 <= n <= left
+        plan.append(n)
+        left -= n
+    assert sum(plan) == S
+    assert all(a >= b for a, b in zip(plan, plan[1:-1]))          # non-increasing up to the last (which may absorb a rest)
+    assert all(n <= hi + lo for n in plan)
+    assert all(n >= min(lo, S) for n in plan)
+    assert L.amcmc_host_chunk_samples(0, thin) == 0 and L.amcmc_host_chunk_samples(10, 0) == 0
