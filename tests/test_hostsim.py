@@ -73,3 +73,24 @@ def test_asss_kernel_body_matches_oracle(hostsim, dt, tol):
     assert np.quantile(err, 0.9) < tol
     good = err < 10 * tol
     np.testing.assert_allclose(s1.adapt_state.scale[good], s2.adapt_state.scale[good], rtol=10 * tol, atol=10 * tol)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel", ["arwmh", "asss"])
+def test_range_split_with_slot_handoff_is_bit_identical(hostsim, dt, kernel):
+    """the balanced launch cuts a run into ranges and parks the chain's registers raw in a slot between them: any cut must give
+    the same samples, decisions and final state bit for bit (collection points inside, at and across the cuts; warm-up restart
+    inside a range; frozen template)"""
+    from oracle import arwmh_numpy as o, c_oracle as co
+    C, T = 40, 173
+    st = o.arwmh_init(o.make_potential("eight_schools"), co.init_uniform(7, C, 10, dt=dt))
+    for adapt in ((True, False) if kernel == "arwmh" else (True,)):
+        kw = dict(seed=9, chain_offset=3, num_warmup=50, thinning=7, collect_start=4, adapt=adapt, kernel=kernel)
+        s1, o1 = hostsim.run_es(st, T, **kw)
+        for seg in (1, 7, 16, 50, 172, 400):
+            s2, o2 = hostsim.run_es(st, T, split=seg, **kw)
+            for k in ("z", "potential_energy", "accepts"):
+                assert np.array_equal(o1[k], o2[k]), (seg, k)
+            assert np.array_equal(s1.z, s2.z) and np.array_equal(s1.potential_energy, s2.potential_energy)
+            assert np.array_equal(s1.adapt_state.scale, s2.adapt_state.scale) and np.array_equal(s1.as_change, s2.as_change)
+            assert np.array_equal(s1.adapt_state.loc, s2.adapt_state.loc)
