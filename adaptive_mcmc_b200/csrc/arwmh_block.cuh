@@ -11,6 +11,7 @@
 // with Lt unit lower triangular, stored COLUMN-MAJOR packed so that "thread i <-> row i" accesses
 // of a fixed column are contiguous (bank-conflict free).
 #pragma once
+#include <cooperative_groups.h>
 #include "arwmh_small.cuh"
 
 namespace amcmc {
@@ -55,11 +56,14 @@ template <typename R> struct DiamondsBlockModel {
   const R* __restrict__ Y;    // [n]
   double cst;
 
-  template <int NT> __device__ R potential(const R* q, R* red) const {
+  static constexpr bool kRowSplit = true;  // the likelihood is a sum over data rows: two CTAs of a cluster can share it
+
+  // sum of squared residuals over rows [r_begin, r_end), reduced over the CTA (every thread gets the sum)
+  template <int NT> __device__ R rss_rows(const R* q, R* red, int r_begin, int r_end) const {
     const R icpt = q[0];
     R ss0 = 0, ss1 = 0;
-    int r = threadIdx.x;
-    for (; r + NT < n; r += 2 * NT) {  // two rows in flight per thread
+    int r = r_begin + threadIdx.x;
+    for (; r + NT < r_end; r += 2 * NT) {  // two rows in flight per thread
       R m0 = icpt, m1 = icpt;
       for (int k = 0; k < kc; ++k) {
         const R bk = q[1 + k];
@@ -70,13 +74,17 @@ template <typename R> struct DiamondsBlockModel {
       ss0 = fma(e0, e0, ss0);
       ss1 = fma(e1, e1, ss1);
     }
-    if (r < n) {
+    if (r < r_end) {
       R m0 = icpt;
       for (int k = 0; k < kc; ++k) m0 = fma(__ldg(XcT + (size_t)k * n_stride + r), q[1 + k], m0);
       const R e0 = __ldg(Y + r) - m0;
       ss0 = fma(e0, e0, ss0);
     }
-    const R rss = block_sum<R, NT>(ss0 + ss1, red);
+    return block_sum<R, NT>(ss0 + ss1, red);
+  }
+
+  __device__ R finish(const R* q, R rss) const {
+    const R icpt = q[0];
     R sb = 0;
     for (int k = 0; k < kc; ++k) sb = fma(q[1 + k], q[1 + k], sb);
     const R s = q[1 + kc];
@@ -90,6 +98,8 @@ template <typename R> struct DiamondsBlockModel {
     return (R)((double)((R)0.5 * sb + (R)2 * Num<R>::log1p(ti * ti * third) + (R)2 * Num<R>::log1p(ts * ts * third)) +
                ((double)n - 1.0) * (double)s + cst + inv2var * (double)rss);
   }
+
+  template <int NT> __device__ R potential(const R* q, R* red) const { return finish(q, rss_rows<NT>(q, red, 0, n)); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -197,14 +207,22 @@ template <typename R> __device__ __forceinline__ R frob2_warp(const BlockSmem<R>
   return warp_sum(col);
 }
 
-template <class BM, typename R, bool ADAPT, bool EXTERNAL, int NT>
+// CL = 2 (few-chain diamonds runs, launched with a cluster dimension of 2): two CTAs carry the SAME chain -- identical draws,
+// proposals, decisions and adaptation, so no state is exchanged -- and split the data rows of the likelihood; the two partial
+// sums of squared residuals cross through distributed shared memory (one cluster barrier per step, two slot sets alternate)
+// and are added in rank order in both CTAs.  Rank 0 writes the outputs.
+template <class BM, typename R, bool ADAPT, bool EXTERNAL, int NT, int CL = 1>
 __global__ void __launch_bounds__(NT)
 arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const int d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ R cl_xch[2][2];
   BlockSmem<R> sm(smem_raw, d);
   const int tid = threadIdx.x;
   const int64_t C = st.C;
-  const int64_t c = blockIdx.x;
+  const int64_t c = blockIdx.x / CL;
+  const int cl_rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
+  const bool lead = cl_rank == 0;
+  if (CL > 1) cooperative_groups::this_cluster().sync();  // the peer's exchange slots exist
   // ---- load the chain: L (row-major packed, with diagonal) -> Lt (column-major packed), Dg
   for (int k = tid; k < d; k += NT) {
     sm.x[k] = st.z[k * C + c];
@@ -262,7 +280,20 @@ arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const 
     }
     __syncthreads();
     // ---- potential, accept (:170-178); every thread holds the same scalars
-    R Up = m.template potential<NT>(sm.xp, sm.red);
+    R Up;
+    if constexpr (CL > 1) {
+      cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+      const int half = (m.n / 2 + 31) & ~31, par = (int)(t & 1);
+      const R part = m.template rss_rows<NT>(sm.xp, sm.red, cl_rank == 0 ? 0 : half, cl_rank == 0 ? half : m.n);
+      if (tid == 0) {
+        cl_xch[par][cl_rank] = part;
+        *cluster.map_shared_rank(&cl_xch[par][cl_rank], cl_rank ^ 1) = part;
+      }
+      cluster.sync();
+      Up = m.finish(sm.xp, cl_xch[par][0] + cl_xch[par][1]);
+    } else {
+      Up = m.template potential<NT>(sm.xp, sm.red);
+    }
     if (Num<R>::isnan(Up)) Up = Num<R>::inf();
     const R e = Num<R>::exp(U - Up);
     const R alpha = (e > (R)1) ? (R)1 : e;
@@ -271,7 +302,7 @@ arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const 
       for (int k = tid; k < d; k += NT) sm.x[k] = sm.xp[k];
       U = Up;
     }
-    if (a.out_acc && tid == 0) a.out_acc[t * C + c] = (uint8_t)acc;
+    if (a.out_acc && tid == 0 && lead) a.out_acc[t * C + c] = (uint8_t)acc;
     const int64_t n = (it < a.num_warmup) ? (it + 1) : (it + 1 - a.num_warmup);
     // :185 running mean over n; the frozen kernel (sample_Pnx, pooled windows) reports the mean over THIS launch
     const R nf = (R)n;
@@ -305,12 +336,14 @@ arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const 
     }
     if (--until_collect == 0) {
       until_collect = a.thinning;
-      if (a.out_z)
+      if (a.out_z && lead)
         for (int k = tid; k < d; k += NT) a.out_z[(sidx * d + k) * C + c] = sm.x[k];
-      if (a.out_pe && tid == 0) a.out_pe[sidx * C + c] = U;
+      if (a.out_pe && tid == 0 && lead) a.out_pe[sidx * C + c] = U;
       ++sidx;
     }
   }
+  if (CL > 1) cooperative_groups::this_cluster().sync();  // nobody leaves while the peer may still write into its slots
+  if (!lead) return;
   // ---- store
   __syncthreads();
   for (int k = tid; k < d; k += NT) st.z[k * C + c] = sm.x[k];

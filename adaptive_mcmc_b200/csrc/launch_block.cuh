@@ -1,11 +1,17 @@
 // launch_block.cuh -- host-side launch helpers for the block-per-chain kernels.
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 #include "arwmh_block.cuh"
 #include "asss_block.cuh"
 #include "launch_small.cuh"
 
 namespace amcmc {
+
+// models whose likelihood is a sum over data rows that two CTAs can share declare `static constexpr bool kRowSplit = true`
+// and provide rss_rows<NT>(q, red, r_begin, r_end) / finish(q, rss)
+template <class BM, class = void> struct has_row_split : std::false_type {};
+template <class BM> struct has_row_split<BM, std::void_t<decltype(BM::kRowSplit)>> : std::bool_constant<BM::kRowSplit> {};
 
 template <class K> inline int ensure_smem(K kernel, size_t bytes) {
   if (bytes <= 48 * 1024) return AMCMC_OK;
@@ -51,6 +57,37 @@ int launch_block_run(const BM& m, int d, const amcmc_state* st, const amcmc_run_
     else          { if (ext) AMCMC_LA(true, false); else AMCMC_LA(false, false); }  // frozen: ASSS.sample_Pnx
 #undef AMCMC_LA
     return check_cuda(cudaGetLastError(), "asss_block_kernel launch");
+  }
+  // Few-chain diamonds (at most one chain per TWO SMs): a 2-CTA cluster per chain splits the data rows of the likelihood
+  // (arwmh_block.cuh, CL = 2).  AMCMC_BLOCK_CLUSTER=0/1 overrides.
+  if constexpr (has_row_split<BM>::value) {
+    const char* cl_e = getenv("AMCMC_BLOCK_CLUSTER");  // read per launch: tests switch it inside one process
+    const int cl_env = cl_e ? atoi(cl_e) : -1;
+    const bool cl2 = cl_env >= 0 ? cl_env != 0 : (2 * st->n_chains <= (int64_t)sms && a->n_steps > 0);
+    if (cl2) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * grid);
+      cfg.blockDim = dim3(kBlockThreadsWide);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+#define AMCMC_LC(AD, EX)                                                              \
+  do {                                                                                \
+    auto k = arwmh_block_kernel<BM, R, AD, EX, kBlockThreadsWide, 2>;                 \
+    if ((rc = ensure_smem(k, smem))) return rc;                                       \
+    rc = check_cuda(cudaLaunchKernelEx(&cfg, k, m, sv, rv, d), "arwmh_block_kernel (cluster) launch"); \
+  } while (0)
+      if (a->adapt) { if (ext) AMCMC_LC(true, true); else AMCMC_LC(true, false); }
+      else          { if (ext) AMCMC_LC(false, true); else AMCMC_LC(false, false); }
+#undef AMCMC_LC
+      return rc;
+    }
   }
 #define AMCMC_LB(AD, EX)                                                              \
   do {                                                                                \

@@ -192,3 +192,39 @@ def test_ram_adapts_to_target_shape():
     # the chain actually samples N(0, Sigma): pooled marginal variance of the kept draws is O(1)
     x = coll["z"]["x"][-5:].double()
     assert 0.3 < float(x.var()) < 3.0
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_two_cta_cluster_per_chain_matches_the_single_cta_kernel(prec, monkeypatch):
+    """few-chain diamonds: two CTAs of a cluster carry the same chain and split the data rows of the likelihood (arwmh_block.cuh,
+    CL = 2).  The only difference to the one-CTA kernel is the order in which the 5000 squared residuals are added: fp64 --
+    identical decisions and 1e-9 on the positions over 300 steps; fp32 -- energies of a fixed state agree to 1e-5 relative
+    and the chains stay statistically the same (the trajectories themselves part after a first flipped decision)."""
+    import adaptive_mcmc_b200 as am
+    from adaptive_mcmc_b200 import _lib, models
+
+    tdt = torch.float64 if prec == "f64" else torch.float32
+    data = models.synthetic_diamonds(n=5000, k=25, seed=0)
+    outs = []
+    for cl in ("0", "1"):
+        monkeypatch.setenv("AMCMC_BLOCK_CLUSTER", cl)
+        s = am.ARWMH(models.diamonds, num_chains=24, dtype=tdt)
+        s.impl = _lib.IMPL_BLOCK
+        b = s._batch_from_state(s.init(5, num_warmup=100, init_params=None, model_kwargs=data))
+        raw = s.run_batch(b, 300, thinning=10, collect_start=5, record_accept=True)
+        outs.append((raw["accept"].cpu().numpy(), raw["z"].cpu().numpy(), raw["potential_energy"].cpu().numpy(), b.scale.cpu().numpy(),
+                     float(b.macc.mean())))
+    a0, z0, u0, sc0, m0 = outs[0]
+    a1, z1, u1, sc1, m1 = outs[1]
+    if prec == "f64":
+        assert (a0 == a1).all()
+        np.testing.assert_allclose(z1, z0, rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(sc1, sc0, rtol=1e-8, atol=1e-10)
+    else:
+        np.testing.assert_allclose(u1[0], u0[0], rtol=1e-5)          # first sample: before rounding differences can flip a decision
+        same = (a0 == a1).all(axis=0)
+        assert same.mean() >= 0.5 and abs(m0 - m1) < 0.03
+        # identical decisions, but alpha = exp(U - U') feeds the step-size recursion: the proposals drift apart at the 1e-6 level
+        # per step and the far-from-the-mode transient of these 300 steps amplifies it
+        err = np.abs(z1[:, :, same] - z0[:, :, same]) / (1 + np.abs(z0[:, :, same]))
+        assert err.max() < 5e-2 and np.median(err) < 1e-3, (err.max(), np.median(err))
