@@ -207,15 +207,15 @@ template <typename R> __device__ __forceinline__ R frob2_warp(const BlockSmem<R>
   return warp_sum(col);
 }
 
-// CL = 2 (few-chain diamonds runs, launched with a cluster dimension of 2): two CTAs carry the SAME chain -- identical draws,
-// proposals, decisions and adaptation, so no state is exchanged -- and split the data rows of the likelihood; the two partial
+// CL = 2, 4, 8 (few-chain diamonds runs, launched with that cluster dimension): the CTAs of a cluster carry the SAME chain -- identical draws,
+// proposals, decisions and adaptation, so no state is exchanged -- and split the data rows of the likelihood; the partial
 // sums of squared residuals cross through distributed shared memory (one cluster barrier per step, two slot sets alternate)
-// and are added in rank order in both CTAs.  Rank 0 writes the outputs.
+// and are added in rank order in every CTA.  Rank 0 writes the outputs.
 template <class BM, typename R, bool ADAPT, bool EXTERNAL, int NT, int CL = 1>
 __global__ void __launch_bounds__(NT)
 arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const int d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ R cl_xch[2][2];
+  __shared__ R cl_xch[2][CL];
   BlockSmem<R> sm(smem_raw, d);
   const int tid = threadIdx.x;
   const int64_t C = st.C;
@@ -283,14 +283,15 @@ arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const 
     R Up;
     if constexpr (CL > 1) {
       cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
-      const int half = (m.n / 2 + 31) & ~31, par = (int)(t & 1);
-      const R part = m.template rss_rows<NT>(sm.xp, sm.red, cl_rank == 0 ? 0 : half, cl_rank == 0 ? half : m.n);
-      if (tid == 0) {
-        cl_xch[par][cl_rank] = part;
-        *cluster.map_shared_rank(&cl_xch[par][cl_rank], cl_rank ^ 1) = part;
-      }
+      const int share = ((m.n + CL - 1) / CL + 31) & ~31, par = (int)(t & 1);
+      const int r0 = min(m.n, cl_rank * share), r1 = min(m.n, r0 + share);
+      const R part = m.template rss_rows<NT>(sm.xp, sm.red, r0, r1);
+      if (tid < CL) *cluster.map_shared_rank(&cl_xch[par][cl_rank], tid) = part;  // my partial into every CTA of the cluster
       cluster.sync();
-      Up = m.finish(sm.xp, cl_xch[par][0] + cl_xch[par][1]);
+      R rss = cl_xch[par][0];
+#pragma unroll
+      for (int k = 1; k < CL; ++k) rss += cl_xch[par][k];  // rank order: the same sum in every CTA
+      Up = m.finish(sm.xp, rss);
     } else {
       Up = m.template potential<NT>(sm.xp, sm.red);
     }

@@ -58,34 +58,74 @@ int launch_block_run(const BM& m, int d, const amcmc_state* st, const amcmc_run_
 #undef AMCMC_LA
     return check_cuda(cudaGetLastError(), "asss_block_kernel launch");
   }
-  // Few-chain diamonds (at most one chain per TWO SMs): a 2-CTA cluster per chain splits the data rows of the likelihood
-  // (arwmh_block.cuh, CL = 2).  AMCMC_BLOCK_CLUSTER=0/1 overrides.
+  // Few-chain diamonds (at most one chain per TWO SMs): a thread-block cluster per chain splits the data rows of the
+  // likelihood (arwmh_block.cuh, CL = 2, 4, 8).  AMCMC_BLOCK_CLUSTER=0/2/4/8 overrides.
   if constexpr (has_row_split<BM>::value) {
     const char* cl_e = getenv("AMCMC_BLOCK_CLUSTER");  // read per launch: tests switch it inside one process
     const int cl_env = cl_e ? atoi(cl_e) : -1;
-    const bool cl2 = cl_env >= 0 ? cl_env != 0 : (2 * st->n_chains <= (int64_t)sms && a->n_steps > 0);
-    if (cl2) {
+    // CTAs per chain: the largest cluster size whose clusters are all co-resident (a cluster lives inside one GPC, so fewer
+    // clusters of 8 fit than SMs / 8: measured 18 chains x 8 CTAs = two waves, 14.1 us per step instead of 7.1);
+    // cudaOccupancyMaxActiveClusters answers per cluster size, cached per device.  The environment variable gives the
+    // cluster size directly (0 or 1: none).
+    static int max_clusters[64][3] = {};  // [device][CL = 2, 4, 8], 0 = not asked yet, -1 = unavailable
+    int cl = 1;
+    if (a->n_steps > 0 && dev >= 0 && dev < 64) {
+      const int sizes[3] = {2, 4, 8};
+      for (int k = 2; k >= 0 && cl == 1; --k) {
+        if (max_clusters[dev][k] == 0) {
+          cudaLaunchConfig_t q = {};
+          q.gridDim = dim3((unsigned)(sizes[k] * sms));
+          q.blockDim = dim3(kBlockThreadsWide);
+          q.dynamicSmemBytes = smem;
+          cudaLaunchAttribute qa[1];
+          qa[0].id = cudaLaunchAttributeClusterDimension;
+          qa[0].val.clusterDim.x = (unsigned)sizes[k];
+          qa[0].val.clusterDim.y = 1;
+          qa[0].val.clusterDim.z = 1;
+          q.attrs = qa;
+          q.numAttrs = 1;
+          int nmax = 0;
+          cudaError_t e = cudaSuccess;
+          if (ensure_smem(arwmh_block_kernel<BM, R, true, false, kBlockThreadsWide, 2>, smem) != AMCMC_OK) e = cudaErrorUnknown;
+          if (e == cudaSuccess) {
+            if (sizes[k] == 8) e = cudaOccupancyMaxActiveClusters(&nmax, arwmh_block_kernel<BM, R, true, false, kBlockThreadsWide, 8>, &q);
+            else if (sizes[k] == 4) e = cudaOccupancyMaxActiveClusters(&nmax, arwmh_block_kernel<BM, R, true, false, kBlockThreadsWide, 4>, &q);
+            else e = cudaOccupancyMaxActiveClusters(&nmax, arwmh_block_kernel<BM, R, true, false, kBlockThreadsWide, 2>, &q);
+          }
+          if (e != cudaSuccess) { cudaGetLastError(); nmax = -1; }
+          max_clusters[dev][k] = nmax > 0 ? nmax : -1;
+        }
+        if (max_clusters[dev][k] >= st->n_chains) cl = sizes[k];
+      }
+    }
+    if (cl_env >= 0) cl = (cl_env == 2 || cl_env == 4 || cl_env == 8) ? cl_env : 1;
+    if (cl > 1 && a->n_steps > 0) {
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(2 * grid);
+      cfg.gridDim = dim3((unsigned)cl * grid);
       cfg.blockDim = dim3(kBlockThreadsWide);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = s;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.x = (unsigned)cl;
       at[0].val.clusterDim.y = 1;
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-#define AMCMC_LC(AD, EX)                                                              \
+#define AMCMC_LC1(AD, EX, CLN)                                                        \
   do {                                                                                \
-    auto k = arwmh_block_kernel<BM, R, AD, EX, kBlockThreadsWide, 2>;                 \
+    auto k = arwmh_block_kernel<BM, R, AD, EX, kBlockThreadsWide, CLN>;               \
     if ((rc = ensure_smem(k, smem))) return rc;                                       \
     rc = check_cuda(cudaLaunchKernelEx(&cfg, k, m, sv, rv, d), "arwmh_block_kernel (cluster) launch"); \
+  } while (0)
+#define AMCMC_LC(AD, EX)                                                              \
+  do {                                                                                \
+    if (cl == 8) AMCMC_LC1(AD, EX, 8); else if (cl == 4) AMCMC_LC1(AD, EX, 4); else AMCMC_LC1(AD, EX, 2); \
   } while (0)
       if (a->adapt) { if (ext) AMCMC_LC(true, true); else AMCMC_LC(true, false); }
       else          { if (ext) AMCMC_LC(false, true); else AMCMC_LC(false, false); }
 #undef AMCMC_LC
+#undef AMCMC_LC1
       return rc;
     }
   }

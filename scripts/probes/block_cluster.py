@@ -1,5 +1,5 @@
 """Few-chain diamonds (BASELINE configs[1] shape: 64 chains): one 512-thread CTA per chain against a 2-CTA cluster per chain.
-AMCMC_BLOCK_CLUSTER=0/1 selects; run once with each."""
+AMCMC_BLOCK_CLUSTER=0/2/4/8 selects the cluster size."""
 import os
 import sys
 import time
@@ -13,7 +13,7 @@ from adaptive_mcmc_b200 import _lib, models
 
 data = models.synthetic_diamonds(n=5000, k=25, seed=0)
 for dt in (torch.float32, torch.float64):
-    for C in (1, 64, 74):
+    for C in (1, 18, 37, 64):
         s = am.ARWMH(models.diamonds, num_chains=C, dtype=dt)
         s.impl = _lib.IMPL_BLOCK
         b = s._batch_from_state(s.init(0, num_warmup=0, init_params=None, model_kwargs=data))

@@ -194,10 +194,11 @@ def test_ram_adapts_to_target_shape():
     assert 0.3 < float(x.var()) < 3.0
 
 
+@pytest.mark.parametrize("cluster", ["2", "4", "8"])
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-def test_two_cta_cluster_per_chain_matches_the_single_cta_kernel(prec, monkeypatch):
-    """few-chain diamonds: two CTAs of a cluster carry the same chain and split the data rows of the likelihood (arwmh_block.cuh,
-    CL = 2).  The only difference to the one-CTA kernel is the order in which the 5000 squared residuals are added: fp64 --
+def test_two_cta_cluster_per_chain_matches_the_single_cta_kernel(prec, cluster, monkeypatch):
+    """few-chain diamonds: the CTAs of a cluster carry the same chain and split the data rows of the likelihood (arwmh_block.cuh,
+    CL = 2, 4, 8).  The only difference to the one-CTA kernel is the order in which the 5000 squared residuals are added: fp64 --
     identical decisions and 1e-9 on the positions over 300 steps; fp32 -- energies of a fixed state agree to 1e-5 relative
     and the chains stay statistically the same (the trajectories themselves part after a first flipped decision)."""
     import adaptive_mcmc_b200 as am
@@ -206,7 +207,7 @@ def test_two_cta_cluster_per_chain_matches_the_single_cta_kernel(prec, monkeypat
     tdt = torch.float64 if prec == "f64" else torch.float32
     data = models.synthetic_diamonds(n=5000, k=25, seed=0)
     outs = []
-    for cl in ("0", "1"):
+    for cl in ("0", cluster):
         monkeypatch.setenv("AMCMC_BLOCK_CLUSTER", cl)
         s = am.ARWMH(models.diamonds, num_chains=24, dtype=tdt)
         s.impl = _lib.IMPL_BLOCK
