@@ -207,6 +207,27 @@ template <typename R> __device__ __forceinline__ R frob2_warp(const BlockSmem<R>
   return warp_sum(col);
 }
 
+// Potential of the CTA's chain with the data rows shared by the CL CTAs of the cluster (CL = 1: the model's own potential).
+// `ncall` counts the calls of this CTA: the exchange slots alternate, so one cluster barrier per call is enough.
+template <class BM, typename R, int NT, int CL>
+__device__ __forceinline__ R cluster_potential(const BM& m, const R* q, R* red, R (*xch)[CL], int cl_rank, unsigned& ncall) {
+  if constexpr (CL > 1) {
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    const int share = ((m.n + CL - 1) / CL + 31) & ~31, par = (int)(ncall & 1u);
+    ++ncall;
+    const int r0 = min(m.n, cl_rank * share), r1 = min(m.n, r0 + share);
+    const R part = m.template rss_rows<NT>(q, red, r0, r1);
+    if (threadIdx.x < CL) *cluster.map_shared_rank(&xch[par][cl_rank], threadIdx.x) = part;  // my partial into every CTA of the cluster
+    cluster.sync();
+    R rss = xch[par][0];
+#pragma unroll
+    for (int k = 1; k < CL; ++k) rss += xch[par][k];  // rank order: the same sum in every CTA
+    return m.finish(q, rss);
+  } else {
+    return m.template potential<NT>(q, red);
+  }
+}
+
 // CL = 2, 4, 8 (few-chain diamonds runs, launched with that cluster dimension): the CTAs of a cluster carry the SAME chain -- identical draws,
 // proposals, decisions and adaptation, so no state is exchanged -- and split the data rows of the likelihood; the partial
 // sums of squared residuals cross through distributed shared memory (one cluster barrier per step, two slot sets alternate)
@@ -222,6 +243,7 @@ arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const 
   const int64_t c = blockIdx.x / CL;
   const int cl_rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
   const bool lead = cl_rank == 0;
+  unsigned cl_calls = 0;
   if (CL > 1) cooperative_groups::this_cluster().sync();  // the peer's exchange slots exist
   // ---- load the chain: L (row-major packed, with diagonal) -> Lt (column-major packed), Dg
   for (int k = tid; k < d; k += NT) {
@@ -280,21 +302,7 @@ arwmh_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const 
     }
     __syncthreads();
     // ---- potential, accept (:170-178); every thread holds the same scalars
-    R Up;
-    if constexpr (CL > 1) {
-      cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
-      const int share = ((m.n + CL - 1) / CL + 31) & ~31, par = (int)(t & 1);
-      const int r0 = min(m.n, cl_rank * share), r1 = min(m.n, r0 + share);
-      const R part = m.template rss_rows<NT>(sm.xp, sm.red, r0, r1);
-      if (tid < CL) *cluster.map_shared_rank(&cl_xch[par][cl_rank], tid) = part;  // my partial into every CTA of the cluster
-      cluster.sync();
-      R rss = cl_xch[par][0];
-#pragma unroll
-      for (int k = 1; k < CL; ++k) rss += cl_xch[par][k];  // rank order: the same sum in every CTA
-      Up = m.finish(sm.xp, rss);
-    } else {
-      Up = m.template potential<NT>(sm.xp, sm.red);
-    }
+    R Up = cluster_potential<BM, R, NT, CL>(m, sm.xp, sm.red, cl_xch, cl_rank, cl_calls);
     if (Num<R>::isnan(Up)) Up = Num<R>::inf();
     const R e = Num<R>::exp(U - Up);
     const R alpha = (e > (R)1) ? (R)1 : e;

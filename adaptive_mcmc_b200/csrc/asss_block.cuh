@@ -15,10 +15,14 @@ namespace amcmc {
 
 #ifdef __CUDACC__
 
-template <class BM, typename R, bool EXTERNAL, bool ADAPT, int NT>
+// CL > 1: the CTAs of a thread-block cluster carry the same chain and share the data rows of every potential evaluation
+// (cluster_potential, arwmh_block.cuh); the shrink loop runs the same number of times in every CTA because all of them see the
+// same energies.
+template <class BM, typename R, bool EXTERNAL, bool ADAPT, int NT, int CL = 1>
 __global__ void __launch_bounds__(NT)
 asss_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const int d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ R cl_xch[2][CL];
   BlockSmem<R> sm(smem_raw, d);
   R* zc = sm.z;      // point on the sphere, first d coordinates
   R* vc = sm.y;      // tangent direction, first d coordinates
@@ -26,7 +30,11 @@ asss_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const i
   R* xb = sm.w;      // scratch: normals of the step, then x_base of the current angle, then delta
   const int tid = threadIdx.x;
   const int64_t C = st.C;
-  const int64_t c = blockIdx.x;
+  const int64_t c = blockIdx.x / CL;
+  const int cl_rank = CL > 1 ? (int)(blockIdx.x % CL) : 0;
+  const bool lead = cl_rank == 0;
+  unsigned cl_calls = 0;
+  if (CL > 1) cooperative_groups::this_cluster().sync();  // the peers' exchange slots exist
   // ---- load the chain (as arwmh_block_kernel)
   for (int k = tid; k < d; k += NT) {
     sm.x[k] = st.z[k * C + c];
@@ -68,7 +76,7 @@ asss_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const i
       sm.xp[i] = acc;
     }
     __syncthreads();
-    Un = m.template potential<NT>(sm.xp, sm.red);
+    Un = cluster_potential<BM, R, NT, CL>(m, sm.xp, sm.red, cl_xch, cl_rank, cl_calls);
     R pe = Un + (R)d * Num<R>::log(om);
     if (Num<R>::isnan(pe)) pe = Num<R>::inf();
     return pe;
@@ -200,12 +208,14 @@ asss_block_kernel(const BM m, const StateView<R> st, const RunView<R> a, const i
     if (last) asc = sm.scal[3];
     if (--until_collect == 0) {
       until_collect = a.thinning;
-      if (a.out_z)
+      if (a.out_z && lead)
         for (int k = tid; k < d; k += NT) a.out_z[(sidx * d + k) * C + c] = sm.x[k];
-      if (a.out_pe && tid == 0) a.out_pe[sidx * C + c] = U;
+      if (a.out_pe && tid == 0 && lead) a.out_pe[sidx * C + c] = U;
       ++sidx;
     }
   }
+  if (CL > 1) cooperative_groups::this_cluster().sync();  // nobody leaves while a peer may still write into its slots
+  if (!lead) return;
   // ---- store
   __syncthreads();
   for (int k = tid; k < d; k += NT) st.z[k * C + c] = sm.x[k];

@@ -40,24 +40,6 @@ int launch_block_run(const BM& m, int d, const amcmc_state* st, const amcmc_run_
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const bool wide = st->n_chains <= (int64_t)kWideMaxChainsPerSm * sms && !getenv("AMCMC_BLOCK_NARROW");
-  if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
-#define AMCMC_LA(EX, AD)                                                              \
-  do {                                                                                \
-    if (wide) {                                                                       \
-      auto k = asss_block_kernel<BM, R, EX, AD, kBlockThreadsWide>;                   \
-      if ((rc = ensure_smem(k, smem))) return rc;                                     \
-      k<<<grid, kBlockThreadsWide, smem, s>>>(m, sv, rv, d);                          \
-    } else {                                                                          \
-      auto k = asss_block_kernel<BM, R, EX, AD, kBlockThreads>;                       \
-      if ((rc = ensure_smem(k, smem))) return rc;                                     \
-      k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);                              \
-    }                                                                                 \
-  } while (0)
-    if (a->adapt) { if (ext) AMCMC_LA(true, true); else AMCMC_LA(false, true); }
-    else          { if (ext) AMCMC_LA(true, false); else AMCMC_LA(false, false); }  // frozen: ASSS.sample_Pnx
-#undef AMCMC_LA
-    return check_cuda(cudaGetLastError(), "asss_block_kernel launch");
-  }
   // Few-chain diamonds (at most one chain per TWO SMs): a thread-block cluster per chain splits the data rows of the
   // likelihood (arwmh_block.cuh, CL = 2, 4, 8).  AMCMC_BLOCK_CLUSTER=0/2/4/8 overrides.
   if constexpr (has_row_split<BM>::value) {
@@ -112,22 +94,45 @@ int launch_block_run(const BM& m, int d, const amcmc_state* st, const amcmc_run_
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-#define AMCMC_LC1(AD, EX, CLN)                                                        \
+#define AMCMC_LC1(KERN, T1, T2, CLN)                                                   \
   do {                                                                                \
-    auto k = arwmh_block_kernel<BM, R, AD, EX, kBlockThreadsWide, CLN>;               \
+    auto k = KERN<BM, R, T1, T2, kBlockThreadsWide, CLN>;                             \
     if ((rc = ensure_smem(k, smem))) return rc;                                       \
-    rc = check_cuda(cudaLaunchKernelEx(&cfg, k, m, sv, rv, d), "arwmh_block_kernel (cluster) launch"); \
+    rc = check_cuda(cudaLaunchKernelEx(&cfg, k, m, sv, rv, d), #KERN " (cluster) launch"); \
   } while (0)
-#define AMCMC_LC(AD, EX)                                                              \
+#define AMCMC_LC(KERN, T1, T2)                                                        \
   do {                                                                                \
-    if (cl == 8) AMCMC_LC1(AD, EX, 8); else if (cl == 4) AMCMC_LC1(AD, EX, 4); else AMCMC_LC1(AD, EX, 2); \
+    if (cl == 8) AMCMC_LC1(KERN, T1, T2, 8); else if (cl == 4) AMCMC_LC1(KERN, T1, T2, 4); else AMCMC_LC1(KERN, T1, T2, 2); \
   } while (0)
-      if (a->adapt) { if (ext) AMCMC_LC(true, true); else AMCMC_LC(true, false); }
-      else          { if (ext) AMCMC_LC(false, true); else AMCMC_LC(false, false); }
+      if (a->kernel_kind == AMCMC_KERNEL_ASSS) {  // template order <EXTERNAL, ADAPT>
+        if (a->adapt) { if (ext) AMCMC_LC(asss_block_kernel, true, true); else AMCMC_LC(asss_block_kernel, false, true); }
+        else          { if (ext) AMCMC_LC(asss_block_kernel, true, false); else AMCMC_LC(asss_block_kernel, false, false); }
+      } else {                                    // template order <ADAPT, EXTERNAL>
+        if (a->adapt) { if (ext) AMCMC_LC(arwmh_block_kernel, true, true); else AMCMC_LC(arwmh_block_kernel, true, false); }
+        else          { if (ext) AMCMC_LC(arwmh_block_kernel, false, true); else AMCMC_LC(arwmh_block_kernel, false, false); }
+      }
 #undef AMCMC_LC
 #undef AMCMC_LC1
       return rc;
     }
+  }
+  if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
+#define AMCMC_LA(EX, AD)                                                              \
+  do {                                                                                \
+    if (wide) {                                                                       \
+      auto k = asss_block_kernel<BM, R, EX, AD, kBlockThreadsWide>;                   \
+      if ((rc = ensure_smem(k, smem))) return rc;                                     \
+      k<<<grid, kBlockThreadsWide, smem, s>>>(m, sv, rv, d);                          \
+    } else {                                                                          \
+      auto k = asss_block_kernel<BM, R, EX, AD, kBlockThreads>;                       \
+      if ((rc = ensure_smem(k, smem))) return rc;                                     \
+      k<<<grid, kBlockThreads, smem, s>>>(m, sv, rv, d);                              \
+    }                                                                                 \
+  } while (0)
+    if (a->adapt) { if (ext) AMCMC_LA(true, true); else AMCMC_LA(false, true); }
+    else          { if (ext) AMCMC_LA(true, false); else AMCMC_LA(false, false); }  // frozen: ASSS.sample_Pnx
+#undef AMCMC_LA
+    return check_cuda(cudaGetLastError(), "asss_block_kernel launch");
   }
 #define AMCMC_LB(AD, EX)                                                              \
   do {                                                                                \
