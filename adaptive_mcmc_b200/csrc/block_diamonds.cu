@@ -3,7 +3,7 @@
 // Model: python/scripts/run_diamonds_lr_decay.py:24-40.
 #include <cmath>
 #include <vector>
-#include "launch_block.cuh"
+#include "block_diamonds.cuh"
 
 namespace amcmc {
 
@@ -41,21 +41,8 @@ int create_diamonds(amcmc_model* m, const double* X, int64_t n, int K, const dou
   return AMCMC_OK;
 }
 
-template <typename R> static DiamondsBlockModel<R> make_dm(const amcmc_model* m) {
-  DiamondsBlockModel<R> b;
-  b.d = m->dim;
-  b.kc = m->dim - 2;
-  b.n = (int)m->n_rows;
-  b.n_stride = (int)m->arr_len[0];
-  b.XcT = (const R*)m->d_arr[0];
-  b.Y = (const R*)m->d_arr[1];
-  b.cst = m->cst;
-  return b;
-}
-
 int run_diamonds_block(const amcmc_model* m, const amcmc_state* st, const amcmc_run_args* a, cudaStream_t s) {
-  if (m->dtype == AMCMC_F32) return launch_block_run<DiamondsBlockModel<float>, float>(make_dm<float>(m), m->dim, st, a, s);
-  return launch_block_run<DiamondsBlockModel<double>, double>(make_dm<double>(m), m->dim, st, a, s);
+  return m->dtype == AMCMC_F32 ? run_diamonds_block_f32(m, st, a, s) : run_diamonds_block_f64(m, st, a, s);
 }
 
 int init_diamonds(const amcmc_model* m, const amcmc_state* st, uint64_t seed, int64_t chain_offset, double radius,
