@@ -184,6 +184,7 @@ template <typename R> struct RunView {
   R* out_z;
   R* out_pe;
   uint8_t* out_acc;
+  const R* ring = nullptr;  // arwmh_small_duo_kernel: shared-memory ring [2][D + 1][32] filled by the CTA's producer warp
 };
 
 template <typename R, int D>
@@ -236,9 +237,17 @@ AMCMC_HD void store_chain(const ChainRegs<R, D>& s, const StateView<R>& st, int6
 }
 
 // Draws of one step: external arrays (shared-draw parity mode) or the Philox stream.
-template <typename R, int D, bool EXTERNAL>
+template <typename R, int D, bool EXTERNAL, bool RING = false>
 AMCMC_HD void step_draws(const RunView<R>& a, const Philox& rng, int64_t C, int64_t c, int64_t t, R (&z)[D], R& u) {
-  if (EXTERNAL) {
+  if (RING) {
+#ifdef __CUDA_ARCH__
+    __syncthreads();  // the producer warp has written step t (and this warp is done with the buffer of step t - 1)
+    const R* buf = a.ring + (size_t)(t & 1) * (D + 1) * 32 + (threadIdx.x & 31);
+#pragma unroll
+    for (int k = 0; k < D; ++k) z[k] = buf[k * 32];
+    u = buf[D * 32];
+#endif
+  } else if (EXTERNAL) {
 #pragma unroll
     for (int k = 0; k < D; ++k) z[k] = a.normals[(t * D + k) * C + c];
     u = a.uniforms[t * C + c];
@@ -252,14 +261,14 @@ AMCMC_HD void step_draws(const RunView<R>& a, const Philox& rng, int64_t C, int6
 // of the few-chain latency either, 0.93 us per step for 1 to 100 chains: the step's own dependent chain is the critical path;
 // not kept.)  n follows arwmh.py:180-181 (it restarts at
 // 1 after the warm-up); the frozen kernel (sample_Pnx, pooled windows) averages its acceptance rate over THIS launch.
-template <class Model, typename R, bool ADAPT, bool EXTERNAL>
+template <class Model, typename R, bool ADAPT, bool EXTERNAL, bool RING = false>
 AMCMC_HD void arwmh_steps(ChainRegs<R, Model::D>& s, const Model& m, const RunView<R>& a, const Philox& rng, int64_t C,
                           int64_t c, int64_t t0, int64_t t1) {
   constexpr int D = Model::D;
   for (int64_t t = t0; t < t1; ++t) {
     const int64_t i = a.i0 + t;
     R z[D], u;
-    step_draws<R, D, EXTERNAL>(a, rng, C, c, t, z, u);
+    step_draws<R, D, EXTERNAL, RING>(a, rng, C, c, t, z, u);
     const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
     const R nf = ADAPT ? (R)n : (R)(t + 1);
     const bool acc = arwmh_step<Model, R, ADAPT, false>(s, m, z, u, nf, n == 1, a.lr_decay, a.target, a.eps);
@@ -272,7 +281,7 @@ AMCMC_HD void arwmh_steps(ChainRegs<R, Model::D>& s, const Model& m, const RunVi
 // collect_start + (k+1) thinning steps) so that the hot loop carries no collection bookkeeping, and the last step of the
 // LAUNCH is peeled: it alone computes as_change (arwmh.py:197).  Any split of [0, n_steps) into consecutive ranges gives
 // the same trajectory and the same samples.
-template <class Model, typename R, bool ADAPT, bool EXTERNAL>
+template <class Model, typename R, bool ADAPT, bool EXTERNAL, bool RING = false>
 AMCMC_HD void arwmh_chain_range(ChainRegs<R, Model::D>& s, const Model& m, const RunView<R>& a, const Philox& rng, int64_t C,
                                 int64_t c, int64_t t, int64_t t_end) {
   constexpr int D = Model::D;
@@ -282,12 +291,12 @@ AMCMC_HD void arwmh_chain_range(ChainRegs<R, Model::D>& s, const Model& m, const
   while (t < t_end) {
     const int64_t seg_end = next_collect < t_end ? next_collect : t_end;
     const int64_t hot_end = seg_end < T ? seg_end : T - 1;
-    arwmh_steps<Model, R, ADAPT, EXTERNAL>(s, m, a, rng, C, c, t, hot_end);
+    arwmh_steps<Model, R, ADAPT, EXTERNAL, RING>(s, m, a, rng, C, c, t, hot_end);
     t = hot_end;
     if (seg_end == T) {  // the last step of the launch
       const int64_t i = a.i0 + t;
       R z[D], u;
-      step_draws<R, D, EXTERNAL>(a, rng, C, c, t, z, u);
+      step_draws<R, D, EXTERNAL, RING>(a, rng, C, c, t, z, u);
       const int64_t n = (i < a.num_warmup) ? (i + 1) : (i + 1 - a.num_warmup);
       const R nf = ADAPT ? (R)n : (R)(t + 1);
       const bool acc = arwmh_step<Model, R, ADAPT, true>(s, m, z, u, nf, n == 1, a.lr_decay, a.target, a.eps);
@@ -324,6 +333,41 @@ arwmh_small_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= st.C) return;
   arwmh_chain_run<Model, R, ADAPT, EXTERNAL>(m, st, a, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Few chains: two warps per 32 chains.  With one warp per scheduler a step is bound by that warp's own in-order issue
+// (~700 dependent instructions, 0.93 us per step from 1 to ~5,000 chains), not by any pipe.  Here a second warp of the CTA,
+// on another scheduler, generates the Philox / Box-Muller draws of step t + 1 into a shared-memory ring while the first
+// runs the step t; one block barrier per step hands the buffers over.  Same draws, same arithmetic: every output is equal
+// to arwmh_small_kernel's.
+// ---------------------------------------------------------------------------------------------
+template <class Model, typename R, bool ADAPT>
+__global__ void __launch_bounds__(64) arwmh_small_duo_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
+  constexpr int D = Model::D;
+  __shared__ R ring[2 * (D + 1) * 32];
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t cc = c < st.C ? c : st.C - 1;  // lanes past the end repeat the last chain (barriers stay uniform)
+  const Philox rng(a.seed, (uint64_t)(cc + a.chain_offset));
+  if (threadIdx.x >= 32) {  // producer
+    for (int64_t t = 0; t < a.n_steps; ++t) {
+      R z[D], u;
+      philox_draws<R, D>(rng, (uint64_t)(a.i0 + t), z, u);
+      R* buf = ring + (size_t)(t & 1) * (D + 1) * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < D; ++k) buf[k * 32] = z[k];
+      buf[D * 32] = u;
+      __syncthreads();
+    }
+    return;
+  }
+  RunView<R> a2 = a;
+  a2.ring = ring;
+  ChainRegs<R, D> s;
+  load_chain(s, st, cc);
+  arwmh_chain_range<Model, R, ADAPT, false, true>(s, m, a2, rng, st.C, cc, 0, a.n_steps);
+  if (c < st.C) store_chain<R, D, ADAPT>(s, st, c);
 }
 
 // ---------------------------------------------------------------------------------------------

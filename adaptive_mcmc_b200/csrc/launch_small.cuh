@@ -49,6 +49,24 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
   const int block = 64;
   const unsigned grid = (unsigned)((st->n_chains + block - 1) / block);
   const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
+  // Few chains (up to 6 groups of 32 per SM): a producer warp per 32 chains generates the draws one step ahead
+  // (arwmh_small_duo_kernel).  AMCMC_SMALL_DUO=0/1 overrides (read per launch: tests switch it).
+  if (!ext && a->kernel_kind != AMCMC_KERNEL_ASSS && a->impl != 4 && a->n_steps > 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("AMCMC_SMALL_DUO");
+    const int64_t n_groups = (st->n_chains + 31) / 32;
+    // measured at 10,000 fused steps, chains -> ms (one warp / two warps per group): 4,736 -> 7.19 / 4.74, 9,472 -> 7.19 / 4.79,
+    // 18,944 -> 7.26 / 7.01, 28,416 -> 10.45 / 9.99, 37,888 -> 10.50 / 13.99: up to 6 groups per SM
+    const bool duo = e ? atoi(e) != 0 : (n_groups <= (int64_t)6 * sms && a->n_steps >= 32);
+    if (duo) {
+      const unsigned dgrid = (unsigned)n_groups;
+      if (a->adapt) arwmh_small_duo_kernel<Model, R, true><<<dgrid, 64, 0, s>>>(m, sv, rv);
+      else arwmh_small_duo_kernel<Model, R, false><<<dgrid, 64, 0, s>>>(m, sv, rv);
+      return check_cuda(cudaGetLastError(), "arwmh_small_duo_kernel launch");
+    }
+  }
   // Balanced variant (arwmh_small.cuh): when the chains give every scheduler more than ~2 warps but not a whole number of
   // them, one CTA of 12 worker warps per SM with a work queue keeps all schedulers saturated.  AMCMC_SMALL_BALANCED=0 forces the plain
   // kernel, =1 the balanced one wherever it fits (tests run both).

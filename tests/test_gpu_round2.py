@@ -279,3 +279,24 @@ def test_balanced_kernel_is_the_default_at_the_headline_size_and_refuses_what_do
         res.append((raw["z"].clone(), b.scale.clone(), b.asc.clone()))
     for x, y in zip(*res):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("model,Cn,T,thin,cs", [("eight_schools", 1, 130, 7, 3), ("eight_schools", 100, 257, 50, 0), ("kidiq", 1000, 90, 1, 0),
+                                              ("eight_schools", 4, 64, 64, 0)])
+@pytest.mark.parametrize("adapt", [True, False])
+def test_two_warp_few_chain_kernel_is_bit_identical(model, Cn, T, thin, cs, adapt, monkeypatch):
+    """few chains: a producer warp generates the draws of step t + 1 into a shared-memory ring while the chain's warp runs step t
+    (arwmh_small_duo_kernel).  Same Philox draws and arithmetic as the one-warp kernel: every output must be EQUAL."""
+    pot_model = getattr(models, model)
+    outs = []
+    for duo in ("0", "1"):
+        monkeypatch.setenv("AMCMC_SMALL_DUO", duo)
+        s = am.ARWMH(pot_model, num_chains=Cn)
+        kw = dict(model_kwargs=models.synthetic_kidiq()) if model == "kidiq" else {}
+        b = s._batch_from_state(s.init(11, num_warmup=40, init_params=None, **kw))
+        if not adapt:
+            s.run_batch(b, 50, collect=())
+        raw = s.run_batch(b, T, thinning=thin, collect_start=cs, record_accept=True, adapt=adapt)
+        outs.append({**{k: v.clone() for k, v in raw.items()}, **{f: getattr(b, f).clone() for f in b._FIELDS}})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
