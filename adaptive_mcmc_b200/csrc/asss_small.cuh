@@ -181,7 +181,7 @@ AMCMC_HD void asss_philox_head(const Philox& g, uint64_t step, R (&vn)[D + 1], R
 
 // Steps [t0, t1) of the launch for one chain whose state is in `s`; any split of [0, n_steps) into consecutive ranges gives
 // the same trajectory and samples (the balanced launch of arwmh_small.cuh hands chains from warp to warp between ranges).
-template <class Model, typename R, bool EXTERNAL, bool ADAPT>
+template <class Model, typename R, bool EXTERNAL, bool ADAPT, bool RING = false>
 AMCMC_HD void asss_chain_range(ChainRegs<R, Model::D>& s, const Model& m, const RunView<R>& a, const Philox& rng, int64_t C,
                                int64_t c, int64_t t0, int64_t t1) {
   constexpr int D = Model::D;
@@ -190,7 +190,16 @@ AMCMC_HD void asss_chain_range(ChainRegs<R, Model::D>& s, const Model& m, const 
   for (int64_t t = t0; t < t1; ++t) {
     const int64_t i = a.i0 + t;
     R vn[D + 1], u_t, u_th;
-    if (EXTERNAL) {
+    if (RING) {  // asss_small_duo_kernel: the head draws of the step come from the CTA's producer warp
+#ifdef __CUDA_ARCH__
+      __syncthreads();
+      const R* buf = a.ring + (size_t)(t & 1) * (D + 3) * 32 + (threadIdx.x & 31);
+#pragma unroll
+      for (int k = 0; k < D + 1; ++k) vn[k] = buf[k * 32];
+      u_t = buf[(D + 1) * 32];
+      u_th = buf[(D + 2) * 32];
+#endif
+    } else if (EXTERNAL) {
 #pragma unroll
       for (int k = 0; k < D + 1; ++k) vn[k] = a.normals[(t * (D + 1) + k) * C + c];
       u_t = a.uniforms[(t * kAsssUniforms + 0) * C + c];
@@ -240,6 +249,38 @@ template <class Model, typename R, bool ADAPT, bool EXTERNAL> struct AsssRange {
 };
 
 #ifdef __CUDACC__
+// Few chains: a producer warp generates the head draws (d + 1 normals, u_t, theta_0) of step t + 1 while the chains' warp runs
+// step t (see arwmh_small_duo_kernel); the shrink uniforms stay lazy in the chains' warp.  Every output equal to
+// asss_small_kernel's.
+template <class Model, typename R, bool ADAPT>
+__global__ void __launch_bounds__(64) asss_small_duo_kernel(const Model m, const StateView<R> st, const RunView<R> a) {
+  constexpr int D = Model::D;
+  __shared__ R ring[2 * (D + 3) * 32];
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t cc = c < st.C ? c : st.C - 1;
+  const Philox rng(a.seed, (uint64_t)(cc + a.chain_offset));
+  if (threadIdx.x >= 32) {
+    for (int64_t t = 0; t < a.n_steps; ++t) {
+      R vn[D + 1], u_t, u_th;
+      asss_philox_head<R, D>(rng, (uint64_t)(a.i0 + t), vn, u_t, u_th);
+      R* buf = ring + (size_t)(t & 1) * (D + 3) * 32 + lane;
+#pragma unroll
+      for (int k = 0; k < D + 1; ++k) buf[k * 32] = vn[k];
+      buf[(D + 1) * 32] = u_t;
+      buf[(D + 2) * 32] = u_th;
+      __syncthreads();
+    }
+    return;
+  }
+  RunView<R> a2 = a;
+  a2.ring = ring;
+  ChainRegs<R, D> s;
+  load_chain(s, st, cc);
+  asss_chain_range<Model, R, false, ADAPT, true>(s, m, a2, rng, st.C, cc, 0, a.n_steps);
+  if (c < st.C) store_chain<R, D, ADAPT>(s, st, c);
+}
+
 template <class Model, typename R, bool EXTERNAL, bool ADAPT>
 // 7 resident CTAs of 64 threads per SM (128 registers): 65,536 chains fit in ONE wave, as for arwmh_small_kernel
 __global__ void __launch_bounds__(64, (sizeof(R) == 4 ? 7 : 1))

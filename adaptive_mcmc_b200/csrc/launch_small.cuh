@@ -51,7 +51,7 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
   const bool ext = a->rng_mode == AMCMC_RNG_EXTERNAL;
   // Few chains (up to 6 groups of 32 per SM): a producer warp per 32 chains generates the draws one step ahead
   // (arwmh_small_duo_kernel).  AMCMC_SMALL_DUO=0/1 overrides (read per launch: tests switch it).
-  if (!ext && a->kernel_kind != AMCMC_KERNEL_ASSS && a->impl != 4 && a->n_steps > 0) {
+  if (!ext && a->impl != 4 && a->n_steps > 0) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -62,9 +62,14 @@ int launch_small_run(const Model& m, const amcmc_state* st, const amcmc_run_args
     const bool duo = e ? atoi(e) != 0 : (n_groups <= (int64_t)6 * sms && a->n_steps >= 32);
     if (duo) {
       const unsigned dgrid = (unsigned)n_groups;
-      if (a->adapt) arwmh_small_duo_kernel<Model, R, true><<<dgrid, 64, 0, s>>>(m, sv, rv);
-      else arwmh_small_duo_kernel<Model, R, false><<<dgrid, 64, 0, s>>>(m, sv, rv);
-      return check_cuda(cudaGetLastError(), "arwmh_small_duo_kernel launch");
+      if (a->kernel_kind == AMCMC_KERNEL_ASSS) {
+        if (a->adapt) asss_small_duo_kernel<Model, R, true><<<dgrid, 64, 0, s>>>(m, sv, rv);
+        else asss_small_duo_kernel<Model, R, false><<<dgrid, 64, 0, s>>>(m, sv, rv);
+      } else {
+        if (a->adapt) arwmh_small_duo_kernel<Model, R, true><<<dgrid, 64, 0, s>>>(m, sv, rv);
+        else arwmh_small_duo_kernel<Model, R, false><<<dgrid, 64, 0, s>>>(m, sv, rv);
+      }
+      return check_cuda(cudaGetLastError(), "small duo kernel launch");
     }
   }
   // Balanced variant (arwmh_small.cuh): when the chains give every scheduler more than ~2 warps but not a whole number of

@@ -300,3 +300,19 @@ def test_two_warp_few_chain_kernel_is_bit_identical(model, Cn, T, thin, cs, adap
         outs.append({**{k: v.clone() for k, v in raw.items()}, **{f: getattr(b, f).clone() for f in b._FIELDS}})
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize("Cn,T,thin,adapt", [(3, 120, 7, True), (500, 90, 30, True), (64, 60, 1, False)])
+def test_two_warp_few_chain_asss_is_bit_identical(Cn, T, thin, adapt, monkeypatch):
+    """the slice sampler with its head draws produced one step ahead by a second warp (asss_small_duo_kernel)"""
+    outs = []
+    for duo in ("0", "1"):
+        monkeypatch.setenv("AMCMC_SMALL_DUO", duo)
+        s = am.ASSS(models.eight_schools, num_chains=Cn)
+        b = s._batch_from_state(s.init(4, num_warmup=30, init_params=None))
+        if not adapt:
+            s.run_batch(b, 40, collect=())
+        raw = s.run_batch(b, T, thinning=thin, adapt=adapt)
+        outs.append({**{k: v.clone() for k, v in raw.items()}, **{f: getattr(b, f).clone() for f in b._FIELDS}})
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
